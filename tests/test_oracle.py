@@ -1,0 +1,146 @@
+"""CPU tests of the oracle (oracle/harmony_oracle.cpp).
+
+The reference holds no golden vectors for this path (its tests pin invariants only),
+so the oracle is pinned three ways: (1) the reference's own test invariants
+(/root/reference/tests/testthat/test_integration.R, test_two_variable.R) on the reference's own
+fixtures; (2) agreement with an independent float64 numpy restatement of the vignette's formulas;
+(3) fp32 instance vs fp64 instance.
+"""
+import numpy as np
+import pytest
+
+from harmony_b200 import harmony_options, prepare_inputs
+from helpers import load_cell_lines, make_perms, make_Y0, rel_l2, run_oracle, setup_args, synthetic
+from numpy_restatement import NumpyHarmony
+
+
+def _prep(Z, meta, vars_use, **kw):
+    return prepare_inputs(Z, meta, vars_use, **kw)
+
+
+def test_integration_invariants_cell_lines_small():
+    # test_integration.R:5-26
+    Z, meta = load_cell_lines(small=True)
+    a = _prep(Z, meta, "dataset", theta=1, nclust=50, options=harmony_options(max_iter_cluster=10))
+    o, _, _ = run_oracle(a, make_Y0(Z, 50, 1), 5)
+    N, d, K = 300, 20, 50
+    assert o.get("Y").T.shape == (d, K)
+    assert o.get("Z_corr").T.shape == (d, N) and o.get("Z_orig").T.shape == (d, N)
+    R = o.get("R")
+    assert R.T.shape == (K, N)
+    assert R.min() >= 0 and R.max() <= 1
+    np.testing.assert_allclose(R.sum(axis=1), 1.0, atol=1e-5)
+    assert np.all(np.isfinite(o.get("Z_corr")))
+
+
+def _chi2(o):
+    O, E = o.get("O"), o.get("E")
+    return float((((O - E) ** 2) / E).sum())
+
+
+def test_theta_decreases_chi2_one_covariate():
+    # test_integration.R:29-41
+    Z, meta = load_cell_lines(small=True)
+    a0 = _prep(Z, meta, "dataset", theta=0, nclust=20)
+    a1 = _prep(Z, meta, "dataset", theta=1, nclust=5)
+    o0, _, _ = run_oracle(a0, make_Y0(Z, 20, 2), 2)
+    o1, _, _ = run_oracle(a1, make_Y0(Z, 5, 2), 2)
+    assert _chi2(o0) > _chi2(o1)
+
+
+def test_two_variable_invariants_and_chi2():
+    # test_two_variable.R:5-55 (the arma::inv multi-covariate branch)
+    Z, meta = load_cell_lines(small=False)
+    a = _prep(Z, meta, ["cell_type", "dataset"], theta=[1, 1], nclust=50,
+              options=harmony_options(max_iter_cluster=10))
+    o, _, _ = run_oracle(a, make_Y0(Z, 50, 3), 10)
+    assert o.get("O").shape[0] == 5 and o.get("E").shape[0] == 5
+    R = o.get("R")
+    assert R.min() >= 0 and R.max() <= 1
+    np.testing.assert_allclose(R.sum(axis=1), 1.0, atol=1e-5)
+    assert np.all(np.isfinite(o.get("Z_corr")))
+    lo = _prep(Z, meta, ["cell_type", "dataset"], theta=[0, 0], nclust=20)
+    hi = _prep(Z, meta, ["cell_type", "dataset"], theta=[2, 2], nclust=20)
+    Y0 = make_Y0(Z, 20, 4)
+    olo, _, _ = run_oracle(lo, Y0, 2)
+    ohi, _, _ = run_oracle(hi, Y0, 2)
+    assert _chi2(olo) > _chi2(ohi)
+
+
+def test_E_column_sums_equal_batch_sizes():
+    # doc/detailedWalkthrough.html soft expectation: colSums(E) = N_b
+    Z, meta = load_cell_lines(small=False)
+    a = _prep(Z, meta, "dataset", nclust=5)
+    o, _, _ = run_oracle(a, make_Y0(Z, 5, 5), 1)
+    np.testing.assert_allclose(o.get("E").sum(axis=1), [846, 824, 700], rtol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["small_1cov", "full_2cov", "synth_3cov", "fixed_lambda"])
+def test_oracle_matches_numpy_restatement(case):
+    if case == "small_1cov":
+        Z, meta = load_cell_lines(small=True)
+        a = _prep(Z, meta, "dataset", nclust=5)
+    elif case == "full_2cov":
+        Z, meta = load_cell_lines(small=False)
+        a = _prep(Z, meta, ["cell_type", "dataset"], nclust=20)
+    elif case == "synth_3cov":
+        Z, meta = synthetic(1500, 12, [3, 6, 2], seed=7)
+        a = _prep(Z, meta, ["cov0", "cov1", "cov2"], nclust=12, theta=[2, 1, 0.5])
+    else:
+        Z, meta = load_cell_lines(small=False)
+        a = _prep(Z, meta, ["dataset"], nclust=10, lambda_=1.0)
+    K, T, N = a["K"], a["max_iter_kmeans"], Z.shape[0]
+    Y0 = make_Y0(Z, K, 11)
+    n_iter = 3
+    perms = make_perms(N, n_iter * T, 5).reshape(n_iter, T, N)
+    o64, _, _ = run_oracle(dict(a, epsilon_harmony=-np.inf), Y0, n_iter, double=True, perms=perms)
+    o32, _, _ = run_oracle(dict(a, epsilon_harmony=-np.inf), Y0, n_iter, double=False, perms=perms)
+    s = setup_args(a)
+    ref = NumpyHarmony(s["Z"], s["phi_i"], s["B_vec"], s["sigma"], s["theta"], s["lambda_"], s["alpha"], T, K,
+                       s["block_size"], s["batch_proportion_cutoff"])
+    ref.init_cluster(Y0)
+    for it in range(n_iter):
+        ref.cluster(perms[it])
+        ref.moe_correct_ridge()
+    # fp64 oracle vs independent fp64 numpy: tight
+    assert rel_l2(o64.get("Z_corr"), ref.Z_corr) < 1e-9
+    assert np.abs(o64.get("R") - ref.R).max() < 1e-9
+    assert np.abs(o64.get("Y") - ref.Y).max() < 1e-9
+    assert np.abs(o64.get("O").T - ref.O).max() < 1e-7
+    np.testing.assert_allclose(o64.trace("objective_kmeans"), ref.obj_kmeans, rtol=1e-6)
+    # fp32 oracle (the reference's arithmetic) vs truth
+    assert rel_l2(o32.get("Z_corr"), ref.Z_corr) < 2e-4
+    am32, am64 = o32.get("R").argmax(axis=1), ref.R.argmax(axis=1)
+    assert (am32 != am64).mean() < 0.01
+
+
+def test_small_n_guards():
+    # harmony.cpp:83-91
+    from oracle.oracle import OracleHarmony
+    Z, meta = synthetic(5, 4, [2], seed=1)
+    a = prepare_inputs(Z, meta, "cov0", nclust=2)
+    o = OracleHarmony()
+    with pytest.raises(RuntimeError, match="less than 6 cells"):
+        o.setup(**setup_args(a))
+    Z, meta = synthetic(30, 4, [2], seed=1)
+    a = prepare_inputs(Z, meta, "cov0", nclust=2)
+    o = OracleHarmony()
+    o.setup(**setup_args(a))
+    assert o.L.ho_warned_small(o.h) == 1
+    o.init_cluster_cpp(make_Y0(Z, 2, 0))
+    o.cluster_cpp(make_perms(30, 4, 0))     # block_size 0.2 -> 5 blocks of 6
+    o.moe_correct_ridge_cpp()
+    assert np.all(np.isfinite(o.get("Z_corr")))
+
+
+def test_convergence_semantics():
+    # harmony.cpp:190-200: the numerator is signed
+    Z, meta = load_cell_lines(small=True)
+    a = _prep(Z, meta, "dataset", nclust=5)
+    o, _, iters = run_oracle(a, make_Y0(Z, 5, 1), 10)
+    oh = o.trace("objective_harmony")
+    assert len(oh) == iters + 1
+    assert len(o.trace("kmeans_rounds")) == iters
+    assert len(o.trace("objective_kmeans")) == 1 + 4 * iters
+    last = (oh[-2] - oh[-1]) / abs(oh[-2])
+    assert (last < 1e-2) == (iters < 10 or o.check_convergence(1))
