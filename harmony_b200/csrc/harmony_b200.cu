@@ -1,0 +1,1204 @@
+// harmony_b200.cu — host side of libharmony_b200.so: the C ABI of include/harmony_b200.h on top of the
+// kernels in kernels.cuh.  One hb_handle == one instance of the reference's `harmony` class
+// (/root/reference/src/harmony.h:20-70).  sm_100a only; there is no CPU path.
+#include "../../include/harmony_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+using namespace hb;
+
+// ---- NCCL through dlopen (the process usually already holds torch's libnccl.so.2) ---------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+} g_nccl;
+
+bool load_nccl(std::string* why) {
+  if (g_nccl.ok) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    if (why) *why = "cannot dlopen libnccl.so.2";
+    return false;
+  }
+#define L(sym) *(void**)(&g_nccl.sym) = dlsym(g_nccl.lib, "nccl" #sym)
+  L(GetUniqueId);
+  L(CommInitRank);
+  L(AllReduce);
+  L(AllGather);
+  L(CommDestroy);
+  L(GetErrorString);
+#undef L
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.AllGather && g_nccl.CommDestroy;
+  if (!g_nccl.ok && why) *why = "libnccl lacks required symbols";
+  return g_nccl.ok;
+}
+
+struct Region {
+  double ms = 0;
+  int64_t launches = 0;
+};
+
+// utils.cpp:102-108
+int my_ceil(float num) {
+  int inum = (int)num;
+  if (num == (float)inum) return inum;
+  return inum + 1;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+}  // namespace
+
+struct hb_handle {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::deque<std::string> warnings;
+
+  // problem
+  int64_t N_global = 0, cell_offset = 0, n = 0;
+  bool shard_set = false;
+  int d = 0, K = 0, B = 0, C = 0, J = 0;
+  std::vector<int> B_vec, cov_of;
+  float block_size = 0, epsilon_kmeans = 0, epsilon_harmony = 0, alpha = 0, cutoff = 0;
+  unsigned max_iter_kmeans = 0, window_size = 3;
+  bool lambda_estimation = false, ran_setup = false, ran_init = false;
+  int verbose = 0;
+  uint64_t seed = 0x5eedULL, round_counter = 0;
+  int nb = 0;
+  uint32_t cpb = 0;
+  int half_bits = 1;
+  int (*abort_cb)(void*) = nullptr;
+  void* abort_user = nullptr;
+
+  // device state
+  DevBuf<float> Zo, Zc, U, R, Y, sigma, theta, Pr_b, N_b, lambda, O, E, P, Oacc, acc, S, V, Wfull, scratch, trace_d;
+  DevBuf<double> obj_acc, stage;
+  DevBuf<int> sort_perm, inv_sort, tuple_levels, cov_of_d, tile_cell0, tile_len, tile_tuple, chunk_start,
+      tuple_chunk0, blk_of, order, H, seg_start, tile_base, iscratch, skipped, err_flag;
+  DevBuf<int64_t> perms_d;
+  int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
+  int trace_cap = 0;
+  std::vector<int> tuple_levels_h;  // [J][C]
+  std::vector<int> sort_perm_h;
+
+  // traces (harmony.h:55-56); values are produced on the device and pulled lazily
+  int obj_count = 0;                      // objective evaluations so far (device slots)
+  std::vector<float> obj_vals;            // 4 per slot, host mirror (first obj_synced slots valid)
+  int obj_synced = 0;
+  std::vector<int> harmony_slots;         // objective_harmony[i] = objective_kmeans[harmony_slots[i]]
+  std::vector<int> kmeans_rounds;
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+
+  // instrumentation
+  int64_t launches = 0;
+  bool timing = false;
+  std::map<std::string, Region> regions;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(hb_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  h->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(h, 10, "CUDA error %s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define CKN(call)                                                                                  \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess)                                                                        \
+      return fail(h, 11, "NCCL error %s at %s:%d", g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?", __FILE__, __LINE__); \
+  } while (0)
+#define CKL()                                                                                      \
+  do {                                                                                             \
+    h->launches++;                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess) return fail(h, 10, "kernel launch failed: %s at %s:%d", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int st__ = (expr);       \
+    if (st__ != 0) return st__; \
+  } while (0)
+
+struct RegionScope {
+  hb_handle* h;
+  const char* name;
+  int64_t l0;
+  RegionScope(hb_handle* h_, const char* n) : h(h_), name(n), l0(h_->launches) {
+    if (h->timing) cudaEventRecord(h->ev0, h->stream);
+  }
+  ~RegionScope() {
+    Region& r = h->regions[name];
+    r.launches += h->launches - l0;
+    if (h->timing) {
+      cudaEventRecord(h->ev1, h->stream);
+      cudaEventSynchronize(h->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      r.ms += ms;
+    }
+  }
+};
+
+int grid_for(int64_t work_items, int threads, int cap) {
+  int64_t g = (work_items + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+int allreduce_f(hb_handle* h, float* p, size_t count) {
+  if (h->world <= 1) return 0;
+  CKN(g_nccl.AllReduce(p, p, count, ncclFloat, ncclSum, h->comm, h->stream));
+  return 0;
+}
+int allreduce_d(hb_handle* h, double* p, size_t count) {
+  if (h->world <= 1) return 0;
+  CKN(g_nccl.AllReduce(p, p, count, ncclDouble, ncclSum, h->comm, h->stream));
+  return 0;
+}
+
+int kq_for(int K) {
+  int q = (K + 31) / 32;
+  int kq = 1;
+  while (kq < q) kq <<= 1;
+  return kq;
+}
+
+template <typename F>
+int dispatch_kq(hb_handle* h, int K, F&& f) {
+  switch (kq_for(K)) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 8: return f(std::integral_constant<int, 8>());
+    case 16: return f(std::integral_constant<int, 16>());
+    case 32: return f(std::integral_constant<int, 32>());
+  }
+  return fail(h, 2, "K = %d is not supported (K <= 1024)", K);
+}
+
+// ---- K1 launcher: assignment from centroids (init + cold start) -------------------------------
+int run_assign(hb_handle* h, bool normalise) {
+  RegionScope rs(h, "assign");
+  const int K = h->K, d = h->d, B = h->B;
+  const int KP = (K + 63) & ~63, DP4 = (d + 3) & ~3;
+  CK(cudaMemsetAsync(h->Oacc.p, 0, sizeof(float) * ((size_t)B * K + K), h->stream));
+  AssignArgs a;
+  a.Zc = h->Zc.p;
+  a.Y = h->Y.p;
+  a.sigma = h->sigma.p;
+  a.U = h->U.p;
+  a.R = h->R.p;
+  a.tile_cell0 = h->tile_cell0.p;
+  a.tile_len = h->tile_len.p;
+  a.tile_tuple = h->tile_tuple.p;
+  a.tuple_levels = h->tuple_levels.p;
+  a.O_acc = h->Oacc.p;
+  a.rs_acc = h->Oacc.p + (size_t)B * K;
+  a.obj_acc = h->obj_acc.p;
+  a.ntiles = h->ntiles;
+  a.d = d;
+  a.K = K;
+  a.C = h->C;
+  a.KP = KP;
+  a.normalise = normalise ? 1 : 0;
+  size_t smem = sizeof(float) * ((size_t)DP4 * KP + (size_t)TM * DP4 + (size_t)TM * (KP + 4) + KP + (size_t)NWARP * KP);
+  if (smem > 227 * 1024) return fail(h, 2, "K*d too large for the assignment kernel (needs %zu B shared memory)", smem);
+  int st = dispatch_kq(h, K, [&](auto kq) -> int {
+    constexpr int KQ = decltype(kq)::value;
+    CK(cudaFuncSetAttribute(k_assign<KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assign<KQ>, ASSIGN_THREADS, smem));
+    if (occ < 1) occ = 1;
+    int grid = std::min(h->ntiles, h->num_sms * occ);
+    if (grid < 1) grid = 1;
+    k_assign<KQ><<<grid, ASSIGN_THREADS, smem, h->stream>>>(a);
+    CKL();
+    return 0;
+  });
+  TRY(st);
+  TRY(allreduce_f(h, h->Oacc.p, (size_t)B * K + K));
+  k_assign_finalize<<<(B * K + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * K, h->Pr_b.p,
+                                                                 h->O.p, h->E.p, B, K);
+  CKL();
+  return 0;
+}
+
+int ensure_trace_cap(hb_handle* h, int slots) {
+  if (slots <= h->trace_cap) return 0;
+  int ncap = std::max(1024, h->trace_cap * 2);
+  while (ncap < slots) ncap *= 2;
+  float* np = nullptr;
+  CK(cudaMalloc((void**)&np, sizeof(float) * 4 * (size_t)ncap));
+  if (h->trace_d.p && h->obj_count > 0)
+    CK(cudaMemcpyAsync(np, h->trace_d.p, sizeof(float) * 4 * (size_t)h->obj_count, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->trace_d.p) cudaFree(h->trace_d.p);
+  h->trace_d.p = np;
+  h->trace_d.n = 4 * (size_t)ncap;
+  h->trace_cap = ncap;
+  return 0;
+}
+
+// obj_acc holds this rank's per-cell sums; fold in the K x B cross term and append to the device trace
+int push_objective(hb_handle* h) {
+  TRY(ensure_trace_cap(h, h->obj_count + 1));
+  TRY(allreduce_d(h, h->obj_acc.p, 2));
+  k_objective_finalize<<<1, 256, 0, h->stream>>>(h->O.p, h->E.p, h->theta.p, h->sigma.p, h->obj_acc.p, h->trace_d.p,
+                                                  h->obj_count, h->B, h->K, (double)h->N_global, 1.0);
+  CKL();
+  h->obj_count++;
+  return 0;
+}
+
+int sync_traces(hb_handle* h) {
+  if (h->obj_synced == h->obj_count) return 0;
+  h->obj_vals.resize(4 * (size_t)h->obj_count);
+  CK(cudaMemcpyAsync(h->obj_vals.data() + 4 * (size_t)h->obj_synced, h->trace_d.p + 4 * (size_t)h->obj_synced,
+                     sizeof(float) * 4 * (size_t)(h->obj_count - h->obj_synced), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->obj_synced = h->obj_count;
+  return 0;
+}
+
+// harmony.cpp:173-205
+int check_convergence_host(hb_handle* h, int type, int* out) {
+  TRY(sync_traces(h));
+  float obj_new, obj_old;
+  auto ok = [&](int slot) { return h->obj_vals[4 * (size_t)slot]; };
+  switch (type) {
+    case 0: {
+      if (h->obj_count < (int)h->window_size + 1) return fail(h, 3, "check_convergence(0): not enough objective values");
+      obj_old = 0;
+      obj_new = 0;
+      for (unsigned i = 0; i < h->window_size; i++) {
+        obj_old += ok(h->obj_count - 2 - (int)i);
+        obj_new += ok(h->obj_count - 1 - (int)i);
+      }
+      *out = (std::abs(obj_old - obj_new) / std::abs(obj_old) < h->epsilon_kmeans) ? 1 : 0;
+      return 0;
+    }
+    case 1: {
+      if (h->harmony_slots.size() < 2) return fail(h, 3, "check_convergence(1): not enough objective values");
+      obj_old = ok(h->harmony_slots[h->harmony_slots.size() - 2]);
+      obj_new = ok(h->harmony_slots[h->harmony_slots.size() - 1]);
+      *out = ((obj_old - obj_new) / std::abs(obj_old) < h->epsilon_harmony) ? 1 : 0;
+      return 0;
+    }
+  }
+  *out = 1;
+  return 0;
+}
+
+// ---- update-order plan ---------------------------------------------------------------------------
+int build_plan(hb_handle* h, const int64_t* perm_d /* device, N_global, or null */) {
+  RegionScope rs(h, "plan");
+  const int nb = h->nb, J = h->J, nc = h->nchunks;
+  const int64_t n = h->n;
+  if (perm_d) {
+    CK(cudaMemsetAsync(h->blk_of.p, 0xff, sizeof(int) * (size_t)n, h->stream));
+    k_plan_block_injected<<<grid_for(h->N_global, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, nb, h->blk_of.p, h->err_flag.p);
+    CKL();
+  } else {
+    uint64_t key = hb_mix64(h->seed ^ hb_mix64(h->round_counter + 0x1234567ull));
+    k_plan_block_native<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, nb, h->half_bits, key, h->blk_of.p);
+    CKL();
+  }
+  h->round_counter++;
+  const int wpb = 8;  // warps per block
+  size_t sm = sizeof(int) * (size_t)wpb * nb;
+  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(h->blk_of.p, h->chunk_start.p, nc, nb, h->H.p);
+  CKL();
+  k_scan_exclusive<<<1, 1024, 0, h->stream>>>(h->H.p, (int64_t)nb * nc, nullptr);
+  CKL();
+  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(h->blk_of.p, h->chunk_start.p, nc, nb, h->H.p,
+                                                                     h->order.p);
+  CKL();
+  const int S = nb * J;
+  k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
+                                                                    h->seg_start.p, h->tile_base.p);
+  CKL();
+  k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->seg_start.p, S, h->tile_base.p);
+  CKL();
+  k_scan_exclusive<<<1, 1024, 0, h->stream>>>(h->tile_base.p, (int64_t)S + 1, nullptr);
+  CKL();
+  return 0;
+}
+
+// ---- one update_R sweep (harmony.cpp:269-342) --------------------------------------------------
+int run_update_R(hb_handle* h) {
+  RegionScope rs(h, "update_R");
+  const int K = h->K, B = h->B, nb = h->nb;
+  const int KP = (K + 63) & ~63;
+  const size_t slot = 2 * ((size_t)B * K + K);  // [add_O | add_rs | rem_O | rem_rs]
+  CK(cudaMemsetAsync(h->acc.p, 0, sizeof(float) * 2 * slot, h->stream));
+  StepArgs a;
+  a.U = h->U.p;
+  a.R = h->R.p;
+  a.order = h->order.p;
+  a.seg_start = h->seg_start.p;
+  a.tile_base = h->tile_base.p;
+  a.tuple_levels = h->tuple_levels.p;
+  a.sigma = h->sigma.p;
+  a.P = h->P.p;
+  a.obj_acc = h->obj_acc.p;
+  a.J = h->J;
+  a.K = K;
+  a.C = h->C;
+  a.KP = KP;
+  const int tiles_bound = (int)std::min<int64_t>((h->n / std::max(1, nb)) / TM + h->J + 8, (int64_t)h->num_sms * 8);
+  const int grid = std::max(1, tiles_bound);
+  const size_t sm_col = sizeof(float) * (size_t)NWARP * KP;
+  const size_t sm_upd = sizeof(float) * ((size_t)NWARP * KP + 3 * (size_t)KP);
+  return dispatch_kq(h, K, [&](auto kq) -> int {
+    constexpr int KQ = decltype(kq)::value;
+    for (int j = 0; j <= nb; ++j) {
+      float* sl = h->acc.p + (size_t)(j & 1) * slot;  // slot j = [add_{j-1} | rem_j]
+      float* add_O = sl;
+      float* add_rs = sl + (size_t)B * K;
+      float* rem_O = sl + (size_t)B * K + K;
+      float* rem_rs = rem_O + (size_t)B * K;
+      if (j < nb) {
+        a.blk = j;
+        a.acc_O = rem_O;
+        a.acc_rs = rem_rs;
+        k_block_colsum<KQ><<<grid, ROW_THREADS, sm_col, h->stream>>>(a);
+        CKL();
+      }
+      TRY(allreduce_f(h, sl, slot));
+      k_step_prepare<<<(B * K + 255) / 256, 256, 0, h->stream>>>(h->O.p, h->E.p, add_O, add_rs, rem_O, rem_rs,
+                                                                  h->Pr_b.p, h->theta.p, (j < nb) ? h->P.p : nullptr, B, K);
+      CKL();
+      CK(cudaMemsetAsync(sl, 0, sizeof(float) * slot, h->stream));
+      if (j < nb) {
+        float* nx = h->acc.p + (size_t)((j + 1) & 1) * slot;  // add_j goes to slot j+1
+        a.acc_O = nx;
+        a.acc_rs = nx + (size_t)B * K;
+        k_block_update<KQ><<<grid, ROW_THREADS, sm_upd, h->stream>>>(a);
+        CKL();
+      }
+    }
+    return 0;
+  });
+}
+
+// ---- moe_correct_ridge_cpp (harmony.cpp:345-638) -------------------------------------------------
+int run_correct(hb_handle* h) {
+  const int K = h->K, d = h->d, B = h->B, J = h->J, C = h->C;
+  const int D1 = d + 1;
+  {
+    RegionScope rs(h, "ridge_stats");
+    CK(cudaMemsetAsync(h->S.p, 0, sizeof(float) * (size_t)J * K * D1, h->stream));
+    StatsArgs a;
+    a.R = h->R.p;
+    a.Zo = h->Zo.p;
+    a.tile_cell0 = h->tile_cell0.p;
+    a.tile_len = h->tile_len.p;
+    a.tile_tuple = h->tile_tuple.p;
+    a.S = h->S.p;
+    a.ntiles = h->ntiles;
+    a.d = d;
+    a.K = K;
+    a.KS = (K <= 128) ? K : 128;
+    const int KSP = (a.KS + 7) & ~7, DP = (D1 + 3) & ~3;
+    dim3 block(DP / 4, KSP / 8);
+    if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the statistics kernel", d);
+    a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms * 4 - 1) / (h->num_sms * 4));
+    dim3 grid((h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta, (K + a.KS - 1) / a.KS);
+    size_t smem = sizeof(float) * (size_t)TM * (KSP + DP);
+    CK(cudaFuncSetAttribute(k_ridge_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ridge_stats<<<grid, block, smem, h->stream>>>(a);
+    CKL();
+    TRY(allreduce_f(h, h->S.p, (size_t)J * K * D1));
+  }
+  {
+    RegionScope rs(h, "ridge_solve");
+    SolveArgs a;
+    a.S = h->S.p;
+    a.O = h->O.p;
+    a.E = h->E.p;
+    a.N_b = h->N_b.p;
+    a.lambda = h->lambda_estimation ? nullptr : h->lambda.p;
+    a.tuple_levels = h->tuple_levels.p;
+    a.cov_of = h->cov_of_d.p;
+    a.Y = h->Y.p;
+    a.V = h->V.p;
+    a.Wfull = h->Wfull.p;
+    a.skipped = h->skipped.p;
+    a.scratch = h->scratch.p;
+    a.iscratch = h->iscratch.p;
+    a.err_flag = h->err_flag.p;
+    a.J = J;
+    a.K = K;
+    a.B = B;
+    a.C = C;
+    a.d = d;
+    a.alpha = h->alpha;
+    a.cutoff = h->cutoff;
+    k_ridge_solve<<<K, 256, sizeof(int) * (size_t)(B + C), h->stream>>>(a);
+    CKL();
+  }
+  {
+    RegionScope rs(h, "ridge_apply");
+    ApplyArgs a;
+    a.R = h->R.p;
+    a.Zo = h->Zo.p;
+    a.V = h->V.p;
+    a.Zc = h->Zc.p;
+    a.tile_cell0 = h->tile_cell0.p;
+    a.tile_len = h->tile_len.p;
+    a.tile_tuple = h->tile_tuple.p;
+    a.ntiles = h->ntiles;
+    a.d = d;
+    a.K = K;
+    const int DP = (d + 3) & ~3, KP4 = (K + 3) & ~3;
+    dim3 block(DP / 4, TM / 4);
+    if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the apply kernel", d);
+    size_t smem = sizeof(float) * ((size_t)KP4 * DP + (size_t)TM * KP4);
+    if (smem > 227 * 1024) return fail(h, 2, "K*d too large for the apply kernel (needs %zu B shared memory)", smem);
+    CK(cudaFuncSetAttribute(k_ridge_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms * 4 - 1) / (h->num_sms * 4));
+    int grid = (h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    k_ridge_apply<<<grid, block, smem, h->stream>>>(a);
+    CKL();
+  }
+  return 0;
+}
+
+int check_err_flag(hb_handle* h) {
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (flag) {
+    int z = 0;
+    cudaMemcpyAsync(h->err_flag.p, &z, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (flag == 1) return fail(h, 4, "update order holds an index outside [0, N)");
+    if (flag == 2) return fail(h, 5, "inv(): matrix is singular");
+    return fail(h, 6, "device error flag %d", flag);
+  }
+  return 0;
+}
+
+// rows of a per-cell field, un-sorted and widened to double, through a bounded staging buffer
+int download_rows(hb_handle* h, const float* src, int cols, double* out) {
+  const int64_t n = h->n;
+  const int64_t rows_per = std::max<int64_t>(1, (int64_t)(h->stage.n / (size_t)cols));
+  for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+    int64_t rows = std::min(rows_per, n - r0);
+    k_download_rows<<<grid_for(rows * cols, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, h->stage.p, h->inv_sort.p,
+                                                                                        r0, rows, cols);
+    CKL();
+    CK(cudaMemcpyAsync(out + r0 * cols, h->stage.p, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+int upload_rows(hb_handle* h, const double* in, int cols, float* dst) {
+  const int64_t n = h->n;
+  const int64_t rows_per = std::max<int64_t>(1, (int64_t)(h->stage.n / (size_t)cols));
+  for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+    int64_t rows = std::min(rows_per, n - r0);
+    CK(cudaMemcpyAsync(h->stage.p, in + r0 * cols, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice,
+                       h->stream));
+    k_upload_rows<<<grid_for(rows * cols, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->stage.p, dst, h->inv_sort.p, r0,
+                                                                                      rows, cols);
+    CKL();
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+int download_small(hb_handle* h, const float* src, size_t count, double* out) {
+  std::vector<float> tmp(count);
+  CK(cudaMemcpyAsync(tmp.data(), src, sizeof(float) * count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < count; ++i) out[i] = (double)tmp[i];
+  return 0;
+}
+int upload_small(hb_handle* h, const double* in, size_t count, float* dst) {
+  std::vector<float> tmp(count);
+  for (size_t i = 0; i < count; ++i) tmp[i] = (float)in[i];
+  CK(cudaMemcpyAsync(dst, tmp.data(), sizeof(float) * count, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int hb_version(void) { return 100; }
+
+int hb_create(hb_handle** out, int device) {
+  if (!out) return 1;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return 10;  // no CUDA device: there is no CPU path
+  hb_handle* h = new hb_handle();
+  if (device < 0) cudaGetDevice(&device);
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete h;
+    return 10;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  *out = h;
+  return 0;
+}
+
+void hb_destroy(hb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  cudaStream_t s = h->stream;
+  delete h;  // frees device buffers
+  if (s) cudaStreamDestroy(s);
+}
+
+const char* hb_last_error(const hb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int hb_pop_warning(hb_handle* h, char* buf, size_t cap) {
+  if (!h || h->warnings.empty()) return 0;
+  if (buf && cap) {
+    strncpy(buf, h->warnings.front().c_str(), cap - 1);
+    buf[cap - 1] = 0;
+  }
+  h->warnings.pop_front();
+  return 1;
+}
+
+int hb_comm_unique_id(char id[HB_COMM_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) <= HB_COMM_ID_BYTES, "id size");
+  std::string why;
+  if (!load_nccl(&why)) return 11;
+  ncclUniqueId uid;
+  if (g_nccl.GetUniqueId(&uid) != ncclSuccess) return 11;
+  memset(id, 0, HB_COMM_ID_BYTES);
+  memcpy(id, &uid, sizeof(uid));
+  return 0;
+}
+
+int hb_comm_init(hb_handle* h, int rank, int world_size, const char id[HB_COMM_ID_BYTES]) {
+  if (!h) return 1;
+  if (h->ran_setup) return fail(h, 3, "hb_comm_init must precede hb_setup");
+  if (world_size < 1 || rank < 0 || rank >= world_size) return fail(h, 2, "bad rank/world_size");
+  h->rank = rank;
+  h->world = world_size;
+  if (world_size == 1) return 0;
+  std::string why;
+  if (!load_nccl(&why)) return fail(h, 11, "%s", why.c_str());
+  CK(cudaSetDevice(h->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  CKN(g_nccl.CommInitRank(&h->comm, world_size, uid, rank));
+  return 0;
+}
+
+int hb_set_shard(hb_handle* h, int64_t N_global, int64_t cell_offset) {
+  if (!h) return 1;
+  if (h->ran_setup) return fail(h, 3, "hb_set_shard must precede hb_setup");
+  h->N_global = N_global;
+  h->cell_offset = cell_offset;
+  h->shard_set = true;
+  return 0;
+}
+
+int hb_set_seed(hb_handle* h, uint64_t seed) {
+  if (!h) return 1;
+  h->seed = seed;
+  h->round_counter = 0;
+  return 0;
+}
+
+int hb_set_abort_callback(hb_handle* h, int (*cb)(void*), void* user) {
+  if (!h) return 1;
+  h->abort_cb = cb;
+  h->abort_user = user;
+  return 0;
+}
+
+int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi_i, const int32_t* B_vec, int C,
+             const double* sigma, const double* theta, const double* lambda, double alpha, int max_iter_kmeans,
+             double epsilon_kmeans, double epsilon_harmony, int K, double block_size,
+             double batch_proportion_cutoff, int verbose) {
+  if (!h) return 1;
+  if (h->ran_setup) return fail(h, 3, "setup was already run on this object");
+  if (!Z || !phi_i || !B_vec || !sigma || !theta) return fail(h, 2, "null argument");
+  if (d < 1 || N < 1 || C < 1 || K < 1) return fail(h, 2, "bad dimensions");
+  if (K > 1024) return fail(h, 2, "K = %d is not supported (K <= 1024)", K);
+  if (N > 2000000000LL) return fail(h, 2, "more than 2e9 cells per GPU are not supported");
+  CK(cudaSetDevice(h->device));
+  h->n = N;
+  if (!h->shard_set) {
+    if (h->world > 1) return fail(h, 3, "hb_set_shard is required when world_size > 1");
+    h->N_global = N;
+    h->cell_offset = 0;
+  }
+  const int64_t NG = h->N_global;
+  h->d = d;
+  h->C = C;
+  h->K = K;
+  h->B_vec.assign(B_vec, B_vec + C);
+  h->B = std::accumulate(h->B_vec.begin(), h->B_vec.end(), 0);
+  const int B = h->B;
+  h->cov_of.resize(B);
+  {
+    int b = 0;
+    for (int c = 0; c < C; ++c)
+      for (int l = 0; l < B_vec[c]; ++l) h->cov_of[b++] = c;
+  }
+  // harmony.cpp:83-91
+  if (NG < 6) return fail(h, 1, "Refusing to run with less than 6 cells");
+  if (NG < 40) {
+    h->warnings.push_back("Too few cells. Setting block_size to 0.2");
+    h->block_size = 0.2f;
+  } else {
+    h->block_size = (float)block_size;
+  }
+  h->epsilon_kmeans = (float)epsilon_kmeans;
+  h->epsilon_harmony = (float)epsilon_harmony;
+  h->alpha = (float)alpha;
+  h->cutoff = (float)batch_proportion_cutoff;
+  h->max_iter_kmeans = (unsigned)max_iter_kmeans;
+  h->verbose = verbose;
+  h->lambda_estimation = (lambda == nullptr) || (lambda[0] == -1);  // harmony.cpp:75
+  // update_R block geometry, harmony.cpp:280-281 (float arithmetic on the GLOBAL cell count)
+  h->nb = my_ceil(1.0f / h->block_size);
+  h->cpb = (uint32_t)((float)NG * h->block_size);
+  if (h->cpb == 0) return fail(h, 2, "block_size * N < 1");
+  {
+    int bits = 1;
+    while ((1ull << bits) < (uint64_t)NG) bits++;
+    h->half_bits = (bits + 1) / 2;
+  }
+
+  // ---- joint covariate tuples; cells get sorted by tuple (stable)
+  std::vector<int64_t> lvl_count(B, 0);
+  std::vector<uint64_t> key(N);
+  std::vector<uint64_t> radix(C);
+  {
+    long double prod = 1;
+    for (int c = 0; c < C; ++c) prod *= (long double)B_vec[c];
+    if (prod > 9e18L) return fail(h, 2, "covariate level product overflows 64 bits");
+    uint64_t r = 1;
+    for (int c = C - 1; c >= 0; --c) {
+      radix[c] = r;
+      r *= (uint64_t)B_vec[c];
+    }
+  }
+  {
+    std::vector<int> base(C, 0);
+    for (int c = 1; c < C; ++c) base[c] = base[c - 1] + B_vec[c - 1];
+    for (int64_t i = 0; i < N; ++i) {
+      uint64_t kk = 0;
+      for (int c = 0; c < C; ++c) {
+        int b = phi_i[i * C + c];
+        if (b < base[c] || b >= base[c] + B_vec[c]) return fail(h, 2, "phi row index %d of cell %lld is not a level of covariate %d", b, (long long)i, c);
+        lvl_count[b]++;
+        kk += (uint64_t)(b - base[c]) * radix[c];
+      }
+      key[i] = kk;
+    }
+  }
+  std::vector<uint64_t> uniq(key);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  if (h->world > 1) {
+    // global tuple dictionary = union over ranks; level counts summed over ranks
+    long long cnt = (long long)uniq.size(), maxcnt = 0;
+    DevBuf<long long> dcnt;
+    CK(dcnt.alloc(1));
+    CK(cudaMemcpyAsync(dcnt.p, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllReduce(dcnt.p, dcnt.p, 1, ncclInt64, ncclMax, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&maxcnt, dcnt.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<uint64_t> sendbuf((size_t)maxcnt, ~0ull), recvbuf((size_t)maxcnt * h->world);
+    std::copy(uniq.begin(), uniq.end(), sendbuf.begin());
+    DevBuf<uint64_t> ds, dr;
+    CK(ds.alloc((size_t)maxcnt));
+    CK(dr.alloc((size_t)maxcnt * h->world));
+    CK(cudaMemcpyAsync(ds.p, sendbuf.data(), sizeof(uint64_t) * (size_t)maxcnt, cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllGather(ds.p, dr.p, (size_t)maxcnt, ncclUint64, h->comm, h->stream));
+    CK(cudaMemcpyAsync(recvbuf.data(), dr.p, sizeof(uint64_t) * recvbuf.size(), cudaMemcpyDeviceToHost, h->stream));
+    DevBuf<long long> dl;
+    CK(dl.alloc(B));
+    std::vector<long long> lc(lvl_count.begin(), lvl_count.end());
+    CK(cudaMemcpyAsync(dl.p, lc.data(), sizeof(long long) * B, cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllReduce(dl.p, dl.p, B, ncclInt64, ncclSum, h->comm, h->stream));
+    CK(cudaMemcpyAsync(lc.data(), dl.p, sizeof(long long) * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b) lvl_count[b] = lc[b];
+    uniq.assign(recvbuf.begin(), recvbuf.end());
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    if (!uniq.empty() && uniq.back() == ~0ull) uniq.pop_back();
+  }
+  if (uniq.size() > 1000000) return fail(h, 2, "more than 1e6 distinct covariate tuples are not supported");
+  const int J = (int)uniq.size();
+  h->J = J;
+  h->tuple_levels_h.resize((size_t)J * C);
+  {
+    std::vector<int> base(C, 0);
+    for (int c = 1; c < C; ++c) base[c] = base[c - 1] + B_vec[c - 1];
+    for (int q = 0; q < J; ++q) {
+      uint64_t kk = uniq[q];
+      for (int c = 0; c < C; ++c) {
+        h->tuple_levels_h[(size_t)q * C + c] = base[c] + (int)(kk / radix[c]);
+        kk %= radix[c];
+      }
+    }
+  }
+  std::vector<int> tuple_of(N);
+  std::vector<int64_t> tstart(J + 1, 0);
+  for (int64_t i = 0; i < N; ++i) {
+    int q = (int)(std::lower_bound(uniq.begin(), uniq.end(), key[i]) - uniq.begin());
+    tuple_of[i] = q;
+    tstart[q + 1]++;
+  }
+  for (int q = 0; q < J; ++q) tstart[q + 1] += tstart[q];
+  h->sort_perm_h.resize(N);
+  std::vector<int> inv_sort(N);
+  {
+    std::vector<int64_t> cur(tstart.begin(), tstart.end() - 1);
+    for (int64_t i = 0; i < N; ++i) {
+      int64_t s = cur[tuple_of[i]]++;
+      h->sort_perm_h[s] = (int)i;
+      inv_sort[i] = (int)s;
+    }
+  }
+  // static tiles (<= TM cells of one tuple) and plan chunks (<= CHUNK cells of one tuple)
+  const int CHUNK = 1024;
+  std::vector<int> t_cell0, t_len, t_tuple, c_start, t_chunk0(J, 0);
+  for (int q = 0; q < J; ++q) {
+    for (int64_t s = tstart[q]; s < tstart[q + 1]; s += TM) {
+      t_cell0.push_back((int)s);
+      t_len.push_back((int)std::min<int64_t>(TM, tstart[q + 1] - s));
+      t_tuple.push_back(q);
+    }
+    t_chunk0[q] = (int)c_start.size();
+    for (int64_t s = tstart[q]; s < tstart[q + 1]; s += CHUNK) c_start.push_back((int)s);
+  }
+  c_start.push_back((int)N);  // start of the trailing empty chunk
+  c_start.push_back((int)N);  // and its end
+  h->ntiles = (int)t_cell0.size();
+  h->nchunks = (int)c_start.size() - 1;
+  // tuples without local cells point at the first later chunk (their segments are empty)
+  for (int q = J - 1; q >= 0; --q)
+    if (tstart[q + 1] == tstart[q]) t_chunk0[q] = (q + 1 < J) ? t_chunk0[q + 1] : h->nchunks - 1;
+
+  // ---- device allocations
+  const size_t nK = (size_t)N * K, nd = (size_t)N * d;
+  CK(h->Zo.alloc(nd));
+  CK(h->Zc.alloc(nd));
+  CK(h->U.alloc(nK));
+  CK(h->R.alloc(nK));
+  CK(h->Y.alloc((size_t)K * d));
+  CK(h->sigma.alloc(K));
+  CK(h->theta.alloc(B));
+  CK(h->Pr_b.alloc(B));
+  CK(h->N_b.alloc(B));
+  CK(h->lambda.alloc(B + 1));
+  CK(h->O.alloc((size_t)B * K));
+  CK(h->E.alloc((size_t)B * K));
+  CK(h->P.alloc((size_t)B * K));
+  CK(h->Oacc.alloc((size_t)B * K + K));
+  CK(h->acc.alloc(4 * ((size_t)B * K + K)));
+  CK(h->S.alloc((size_t)J * K * (d + 1)));
+  CK(h->V.alloc((size_t)J * K * d));
+  CK(h->Wfull.alloc((size_t)K * (B + 1) * d));
+  CK(h->scratch.alloc((size_t)K * (2 * (size_t)(B + 1) * (B + 1) + (size_t)(B + 1) * d)));
+  CK(h->iscratch.alloc((size_t)K * (2 * (size_t)B + J)));
+  CK(h->skipped.alloc(K));
+  CK(h->err_flag.alloc(1));
+  CK(h->obj_acc.alloc(2));
+  CK(h->stage.alloc((size_t)8 << 20));  // 64 MiB of doubles
+  CK(h->sort_perm.alloc(N));
+  CK(h->inv_sort.alloc(N));
+  CK(h->tuple_levels.alloc((size_t)J * C));
+  CK(h->cov_of_d.alloc(B));
+  CK(h->tile_cell0.alloc(h->ntiles));
+  CK(h->tile_len.alloc(h->ntiles));
+  CK(h->tile_tuple.alloc(h->ntiles));
+  CK(h->chunk_start.alloc(h->nchunks + 1));
+  CK(h->tuple_chunk0.alloc(J));
+  CK(h->blk_of.alloc(N));
+  CK(h->order.alloc(N));
+  CK(h->H.alloc((size_t)h->nb * h->nchunks));
+  CK(h->seg_start.alloc((size_t)h->nb * J + 1));
+  CK(h->tile_base.alloc((size_t)h->nb * J + 1));
+  CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->O.p, 0, sizeof(float) * (size_t)B * K, h->stream));
+  CK(cudaMemsetAsync(h->E.p, 0, sizeof(float) * (size_t)B * K, h->stream));
+  CK(cudaMemsetAsync(h->Wfull.p, 0, sizeof(float) * (size_t)K * (B + 1) * d, h->stream));
+  CK(cudaMemsetAsync(h->skipped.p, 0, sizeof(int) * K, h->stream));
+  CK(cudaMemsetAsync(h->R.p, 0, sizeof(float) * nK, h->stream));
+  CK(cudaMemsetAsync(h->U.p, 0, sizeof(float) * nK, h->stream));
+  CK(cudaMemsetAsync(h->Y.p, 0, sizeof(float) * (size_t)K * d, h->stream));
+#define UP(buf, vec) CK(cudaMemcpyAsync(h->buf.p, (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, h->stream))
+  UP(sort_perm, h->sort_perm_h);
+  UP(inv_sort, inv_sort);
+  UP(tuple_levels, h->tuple_levels_h);
+  UP(cov_of_d, h->cov_of);
+  UP(tile_cell0, t_cell0);
+  UP(tile_len, t_len);
+  UP(tile_tuple, t_tuple);
+  UP(chunk_start, c_start);
+  UP(tuple_chunk0, t_chunk0);
+  {
+    std::vector<float> f(K);
+    for (int k = 0; k < K; ++k) f[k] = (float)sigma[k];
+    UP(sigma, f);
+    f.resize(B);
+    for (int b = 0; b < B; ++b) f[b] = (float)theta[b];
+    UP(theta, f);
+    std::vector<float> nbv(B), prb(B);
+    for (int b = 0; b < B; ++b) {
+      nbv[b] = (float)lvl_count[b];
+      prb[b] = (float)lvl_count[b] / (float)NG;  // harmony.cpp:67
+    }
+    UP(N_b, nbv);
+    UP(Pr_b, prb);
+    std::vector<float> lam(B + 1, 0.f);
+    if (!h->lambda_estimation)
+      for (int b = 0; b <= B; ++b) lam[b] = (float)lambda[b];
+    UP(lambda, lam);
+    CK(cudaStreamSynchronize(h->stream));
+  }
+#undef UP
+  // Z: double -> float, into tuple-sorted order (harmony.cpp:41); Z_corr = normalise(Z_orig) (:42)
+  TRY(upload_rows(h, Z, d, h->Zo.p));
+  k_normalise_rows<<<grid_for(N * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->Zo.p, h->Zc.p, N, d);
+  CKL();
+  CK(cudaStreamSynchronize(h->stream));
+  h->ran_setup = true;
+  return 0;
+}
+
+int hb_init_cluster(hb_handle* h, const double* Y0) {
+  if (!h) return 1;
+  if (!h->ran_setup) return fail(h, 3, "setup has not been run");
+  CK(cudaSetDevice(h->device));
+  if (!Y0) return fail(h, 7, "native k-means initialisation is not available in this build; pass Y0");
+  // Y = normalise(kmeans_centers(..)) (harmony.cpp:133-136)
+  TRY(upload_small(h, Y0, (size_t)h->K * h->d, h->Y.p));
+  k_normalise_rows<<<grid_for((int64_t)h->K * 32, 256, 64), 256, 0, h->stream>>>(h->Y.p, h->Y.p, h->K, h->d);
+  CKL();
+  CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
+  TRY(run_assign(h, false));
+  TRY(push_objective(h));                       // compute_objective() (:152)
+  h->harmony_slots.push_back(h->obj_count - 1);  // objective_harmony.push_back (:153)
+  h->ran_init = true;
+  return 0;
+}
+
+int hb_cluster(hb_handle* h, const int64_t* update_orders) {
+  if (!h) return 1;
+  if (!h->ran_init) return fail(h, 3, "init_cluster_cpp has not been run");
+  CK(cudaSetDevice(h->device));
+  const unsigned T = h->max_iter_kmeans;
+  if (h->harmony_slots.size() != 1) {  // harmony.cpp:214-228 cold start
+    TRY(run_assign(h, true));
+    CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));  // the cold start does not evaluate the objective
+  }
+  if (update_orders && T > 0) {
+    size_t cnt = (size_t)T * (size_t)h->N_global;
+    if (h->perms_d.n < cnt) CK(h->perms_d.alloc(cnt));
+    CK(cudaMemcpyAsync(h->perms_d.p, update_orders, sizeof(int64_t) * cnt, cudaMemcpyHostToDevice, h->stream));
+  }
+  unsigned iter;
+  for (iter = 0; iter < T; iter++) {
+    if (h->abort_cb && h->abort_cb(h->abort_user)) return -1;  // Progress::check_abort (:233)
+    TRY(build_plan(h, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr));
+    TRY(run_update_R(h));   // :241
+    TRY(push_objective(h));  // :248
+    if (iter > h->window_size) {  // :250-256
+      int conv = 0;
+      TRY(check_convergence_host(h, 0, &conv));
+      if (conv) {
+        iter++;
+        break;
+      }
+    }
+  }
+  if (update_orders) TRY(check_err_flag(h));
+  h->kmeans_rounds.push_back((int)iter);         // :259
+  h->harmony_slots.push_back(h->obj_count - 1);  // :260
+  return 0;
+}
+
+int hb_moe_correct_ridge(hb_handle* h) {
+  if (!h) return 1;
+  if (!h->ran_init) return fail(h, 3, "init_cluster_cpp has not been run");
+  CK(cudaSetDevice(h->device));
+  TRY(run_correct(h));
+  if (h->C > 1) TRY(check_err_flag(h));
+  return 0;
+}
+
+int hb_check_convergence(hb_handle* h, int type) {
+  if (!h) return -1;
+  int out = 1;
+  int st = check_convergence_host(h, type, &out);
+  if (st != 0) return -st;
+  return out;
+}
+
+int hb_compute_objective(hb_handle* h) {
+  if (!h) return 1;
+  if (!h->ran_init) return fail(h, 3, "init_cluster_cpp has not been run");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
+  k_objective_cells<<<grid_for(h->n * 32, ROW_THREADS, h->num_sms * 8), ROW_THREADS, 0, h->stream>>>(
+      h->R.p, h->U.p, h->sigma.p, h->n, h->K, h->obj_acc.p);
+  CKL();
+  return push_objective(h);
+}
+
+int64_t hb_field_size(const hb_handle* h, int field) {
+  if (!h || !h->ran_setup) return 0;
+  switch (field) {
+    case HB_Z_CORR:
+    case HB_Z_ORIG: return (int64_t)h->n * h->d;
+    case HB_R: return (int64_t)h->n * h->K;
+    case HB_Y: return (int64_t)h->K * h->d;
+    case HB_O:
+    case HB_E: return (int64_t)h->K * h->B;
+    case HB_W: return (int64_t)(h->B + 1) * h->d;
+    case HB_PR_B:
+    case HB_THETA: return h->B;
+    case HB_SIGMA: return h->K;
+    case HB_LAMBDA: return (int64_t)h->K * (h->B + 1);
+    case HB_LAMBDA_VEC: return h->B + 1;
+  }
+  return 0;
+}
+
+int hb_get_field(hb_handle* h, int field, double* out) {
+  if (!h) return 1;
+  if (!h->ran_setup) return fail(h, 3, "setup has not been run");
+  if (!out) return fail(h, 2, "null output");
+  CK(cudaSetDevice(h->device));
+  const int K = h->K, B = h->B, d = h->d;
+  switch (field) {
+    case HB_Z_CORR: return download_rows(h, h->Zc.p, d, out);
+    case HB_Z_ORIG: return download_rows(h, h->Zo.p, d, out);
+    case HB_R: return download_rows(h, h->R.p, K, out);
+    case HB_Y: return download_small(h, h->Y.p, (size_t)K * d, out);
+    case HB_O: return download_small(h, h->O.p, (size_t)K * B, out);
+    case HB_E: return download_small(h, h->E.p, (size_t)K * B, out);
+    case HB_PR_B: return download_small(h, h->Pr_b.p, B, out);
+    case HB_THETA: return download_small(h, h->theta.p, B, out);
+    case HB_SIGMA: return download_small(h, h->sigma.p, K, out);
+    case HB_LAMBDA_VEC: return download_small(h, h->lambda.p, B + 1, out);
+    case HB_LAMBDA: {  // getLambda, harmony.cpp:657-669: K x (B+1) column-major
+      std::vector<double> E((size_t)K * B), lam(B + 1);
+      TRY(download_small(h, h->E.p, (size_t)K * B, E.data()));
+      TRY(download_small(h, h->lambda.p, B + 1, lam.data()));
+      for (int k = 0; k < K; ++k) {
+        out[k] = h->lambda_estimation ? 0.0 : lam[0];
+        for (int b = 0; b < B; ++b)
+          out[(size_t)(b + 1) * K + k] =
+              h->lambda_estimation ? (double)((float)E[(size_t)b * K + k] * h->alpha) : lam[b + 1];
+      }
+      return 0;
+    }
+    case HB_W: {  // (B+1) x d column-major; betas of the last cluster that was corrected
+      std::vector<int> sk(K);
+      CK(cudaMemcpyAsync(sk.data(), h->skipped.p, sizeof(int) * K, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      int last = -1;
+      for (int k = 0; k < K; ++k)
+        if (!sk[k]) last = k;
+      std::vector<double> w((size_t)(B + 1) * d, 0.0);
+      if (last >= 0) TRY(download_small(h, h->Wfull.p + (size_t)last * (B + 1) * d, (size_t)(B + 1) * d, w.data()));
+      for (int b = 0; b <= B; ++b)
+        for (int c = 0; c < d; ++c) out[(size_t)c * (B + 1) + b] = w[(size_t)b * d + c];
+      return 0;
+    }
+  }
+  return fail(h, 2, "unknown field %d", field);
+}
+
+int hb_set_field(hb_handle* h, int field, const double* in) {
+  if (!h) return 1;
+  if (!h->ran_setup) return fail(h, 3, "setup has not been run");
+  if (!in) return fail(h, 2, "null input");
+  CK(cudaSetDevice(h->device));
+  const int K = h->K, B = h->B, d = h->d;
+  switch (field) {
+    case HB_Z_CORR: return upload_rows(h, in, d, h->Zc.p);
+    case HB_R: return upload_rows(h, in, K, h->R.p);
+    case HB_Y: return upload_small(h, in, (size_t)K * d, h->Y.p);
+    case HB_O: return upload_small(h, in, (size_t)K * B, h->O.p);
+    case HB_E: return upload_small(h, in, (size_t)K * B, h->E.p);
+    case HB_THETA: return upload_small(h, in, B, h->theta.p);
+    case HB_SIGMA: return upload_small(h, in, K, h->sigma.p);
+    case HB_LAMBDA_VEC:
+      h->lambda_estimation = false;
+      return upload_small(h, in, B + 1, h->lambda.p);
+  }
+  return fail(h, 2, "field %d is not writable", field);
+}
+
+int hb_get_scalar(const hb_handle* h, int which, double* out) {
+  if (!h || !out) return 1;
+  switch (which) {
+    case HB_N: *out = (double)h->N_global; return 0;
+    case HB_N_LOCAL: *out = (double)h->n; return 0;
+    case HB_B: *out = h->B; return 0;
+    case HB_K: *out = h->K; return 0;
+    case HB_D: *out = h->d; return 0;
+    case HB_C: *out = h->C; return 0;
+    case HB_ALPHA: *out = h->alpha; return 0;
+    case HB_MAX_ITER_KMEANS: *out = h->max_iter_kmeans; return 0;
+    case HB_BLOCK_SIZE: *out = h->block_size; return 0;
+    case HB_EPSILON_KMEANS: *out = h->epsilon_kmeans; return 0;
+    case HB_EPSILON_HARMONY: *out = h->epsilon_harmony; return 0;
+    case HB_LAMBDA_ESTIMATION: *out = h->lambda_estimation ? 1 : 0; return 0;
+    case HB_WINDOW_SIZE: *out = h->window_size; return 0;
+  }
+  return 2;
+}
+
+int hb_set_scalar(hb_handle* h, int which, double value) {
+  if (!h) return 1;
+  switch (which) {
+    case HB_ALPHA: h->alpha = (float)value; return 0;
+    case HB_MAX_ITER_KMEANS:
+      if (value < 0) return fail(h, 2, "max_iter_kmeans must be >= 0");
+      h->max_iter_kmeans = (unsigned)value;
+      return 0;
+    case HB_EPSILON_KMEANS: h->epsilon_kmeans = (float)value; return 0;
+    case HB_EPSILON_HARMONY: h->epsilon_harmony = (float)value; return 0;
+  }
+  return fail(h, 2, "scalar %d is not writable", which);
+}
+
+int hb_get_B_vec(const hb_handle* h, int32_t* out) {
+  if (!h || !out) return 1;
+  for (int c = 0; c < h->C; ++c) out[c] = h->B_vec[c];
+  return 0;
+}
+
+int64_t hb_trace(const hb_handle* hc, int trace, double* out, int64_t cap) {
+  hb_handle* h = const_cast<hb_handle*>(hc);
+  if (!h) return -1;
+  if (trace == HB_KMEANS_ROUNDS) {
+    if (out)
+      for (int64_t i = 0; i < (int64_t)h->kmeans_rounds.size() && i < cap; ++i) out[i] = h->kmeans_rounds[i];
+    return (int64_t)h->kmeans_rounds.size();
+  }
+  if (sync_traces(h) != 0) return -1;
+  if (trace >= HB_OBJECTIVE_KMEANS && trace <= HB_OBJECTIVE_KMEANS_CROSS) {
+    if (out)
+      for (int64_t i = 0; i < h->obj_count && i < cap; ++i) out[i] = h->obj_vals[4 * (size_t)i + trace];
+    return h->obj_count;
+  }
+  if (trace == HB_OBJECTIVE_HARMONY) {
+    if (out)
+      for (int64_t i = 0; i < (int64_t)h->harmony_slots.size() && i < cap; ++i)
+        out[i] = h->obj_vals[4 * (size_t)h->harmony_slots[i]];
+    return (int64_t)h->harmony_slots.size();
+  }
+  return -1;
+}
+
+int64_t hb_kernel_launches(const hb_handle* h) { return h ? h->launches : 0; }
+void* hb_stream(const hb_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int hb_synchronize(hb_handle* h) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int hb_region_time(hb_handle* h, const char* region, double* ms, int64_t* launches) {
+  if (!h || !region) return 1;
+  auto it = h->regions.find(region);
+  if (it == h->regions.end()) return 2;
+  if (ms) *ms = it->second.ms;
+  if (launches) *launches = it->second.launches;
+  return 0;
+}
+
+int hb_enable_timing(hb_handle* h, int on) {
+  if (!h) return 1;
+  h->timing = on != 0;
+  return 0;
+}
+
+}  // extern "C"

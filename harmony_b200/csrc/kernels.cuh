@@ -1,0 +1,1068 @@
+// kernels.cuh — CUDA kernels of the Harmony hot loop (sm_100a).  FFMA generation ("v1"): every
+// contraction is a shared-memory-tiled fp32 kernel; they double as the in-repo correctness anchor
+// for the tcgen05 versions.
+//
+// Device data layout (all fp32, row-major, one row per cell; cells are stored sorted by their joint
+// covariate tuple so that a tile of consecutive cells shares its levels):
+//   Zo[n][d]  original embedding (Z_orig, harmony.h:50)     Zc[n][d]  corrected embedding (Z_corr)
+//   U [n][K]  logits -dist/sigma of the current centroids    R [n][K]  soft assignments
+//   Y [K][d]  centroids                                       O,E[B][K] observed / expected counts
+// The reference's dist_mat (K x N, harmony.h:64) is never materialised: dist = -sigma*U.
+#pragma once
+#include "common.cuh"
+
+namespace hb {
+
+constexpr int TM = 64;           // cells per tile in every tiled kernel
+constexpr int ASSIGN_THREADS = 256;
+constexpr int ROW_THREADS = 256;  // 8 warps, one row per warp at a time
+constexpr int NWARP = ROW_THREADS / 32;
+
+// ------------------------------------------------------------------------------------------------
+// setup helpers
+// ------------------------------------------------------------------------------------------------
+// dst[dst_row[r0 + r]][c] = (float)src[r][c]   (double -> float conversion of harmony.cpp:41 fused
+// with the scatter into tuple-sorted order)
+__global__ void k_upload_rows(const double* __restrict__ src, float* __restrict__ dst,
+                              const int* __restrict__ dst_row, int64_t r0, int64_t rows, int cols) {
+  int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / cols;
+    int c = (int)(idx - r * cols);
+    dst[(int64_t)dst_row[r0 + r] * cols + c] = (float)src[idx];
+  }
+}
+// out[r][c] = (double) src[src_row[r0 + r]][c]   (conv_to<RMAT>::from of harmony.cpp:640-650 + un-sort)
+__global__ void k_download_rows(const float* __restrict__ src, double* __restrict__ out,
+                                const int* __restrict__ src_row, int64_t r0, int64_t rows, int cols) {
+  int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / cols;
+    int c = (int)(idx - r * cols);
+    out[idx] = (double)src[(int64_t)src_row[r0 + r] * cols + c];
+  }
+}
+__global__ void k_f2d(const float* __restrict__ src, double* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)src[i];
+}
+__global__ void k_d2f(const double* __restrict__ src, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)src[i];
+}
+__global__ void k_copy_f(const float* __restrict__ src, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = src[i];
+}
+
+// arma::normalise(X, 2, 0) on the rows of X[n][d] (= columns of the reference's d x N matrix); a zero
+// norm divides by 1.  One warp per row.  dst may alias src.
+__global__ void k_normalise_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int d) {
+  int lane = threadIdx.x & 31;
+  int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = w; r < n; r += nw) {
+    const float* x = src + r * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float v = x[c];
+      s += v * v;
+    }
+    s = warp_sum(s);
+    float nrm = sqrtf(s);
+    if (nrm == 0.f) nrm = 1.f;
+    for (int c = lane; c < d; c += 32) dst[r * d + c] = x[c] / nrm;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: assignment from the centroids — harmony.cpp:141-150 (init) and :220-227 (cold start)
+//   Zc <- L2-normalised rows (cold start only), dist = 2(1 - Y^T z), U = -dist/sigma,
+//   R = exp(U)/sum_k exp(U), O[b] += column sums of R per level, rs += row sums (for E),
+//   objective partials sum(R*dist), sum(sigma*R*log R).
+// One CTA = one tile of <= TM consecutive cells that share a covariate tuple.
+// ------------------------------------------------------------------------------------------------
+struct AssignArgs {
+  float* Zc;
+  const float* Y;       // [K][d]
+  const float* sigma;   // [K]
+  float* U;
+  float* R;
+  const int* tile_cell0;  // [ntiles]
+  const int* tile_len;
+  const int* tile_tuple;
+  const int* tuple_levels;  // [J][C]
+  float* O_acc;             // [B][K]
+  float* rs_acc;            // [K]
+  double* obj_acc;          // [0] = sum R*dist, [1] = sum sigma R log R
+  int ntiles, d, K, C, KP;  // KP = K rounded up to a multiple of 64
+  int normalise;
+};
+
+template <int KQ>
+__global__ void __launch_bounds__(ASSIGN_THREADS) k_assign(AssignArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int d = a.d, K = a.K, KP = a.KP, LS = KP + 4;
+  const int DP4 = (d + 3) & ~3;
+  float* Ys = smem;                     // [DP4][KP]  (rows >= d are zero)
+  float* Zs = Ys + (size_t)DP4 * KP;    // [TM][DP4]  (columns >= d are zero)
+  float* Ls = Zs + (size_t)TM * DP4;    // [TM][LS]   dist tile
+  float* sig = Ls + (size_t)TM * LS;    // [KP]
+  float* part = sig + KP;               // [NWARP][KP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int idx = tid; idx < DP4 * KP; idx += ASSIGN_THREADS) {
+    int dd = idx / KP, k = idx - dd * KP;
+    Ys[idx] = (k < K && dd < d) ? a.Y[(size_t)k * d + dd] : 0.f;
+  }
+  for (int k = tid; k < KP; k += ASSIGN_THREADS) sig[k] = (k < K) ? a.sigma[k] : 1.f;
+
+  float okd = 0.f, oent = 0.f;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int cell0 = a.tile_cell0[tile], len = a.tile_len[tile], q = a.tile_tuple[tile];
+    __syncthreads();  // previous tile's epilogue is done with Zs/Ls/part (and Ys/sig are filled)
+    // ---- load (+ normalise) the Z tile into Zs[cell][dd]
+    for (int r = warp; r < TM; r += NWARP) {
+      if (r < len) {
+        float* zrow = a.Zc + (size_t)(cell0 + r) * d;
+        float nrm = 1.f;
+        if (a.normalise) {
+          float s = 0.f;
+          for (int c = lane; c < d; c += 32) {
+            float v = zrow[c];
+            s += v * v;
+          }
+          s = warp_sum(s);
+          nrm = sqrtf(s);
+          if (nrm == 0.f) nrm = 1.f;
+        }
+        for (int c = lane; c < DP4; c += 32) {
+          float v = 0.f;
+          if (c < d) {
+            v = zrow[c];
+            if (a.normalise) {
+              v = v / nrm;
+              zrow[c] = v;
+            }
+          }
+          Zs[r * DP4 + c] = v;
+        }
+      } else {
+        for (int c = lane; c < DP4; c += 32) Zs[r * DP4 + c] = 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- dist tile: Ls[cell][k] = 2 * (1 - z . y_k); thread = 4 cells x 4 clusters per 64-cluster chunk
+    {
+      const int ty = tid >> 4, tx = tid & 15;
+      for (int kc = 0; kc < KP; kc += 64) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const float* zp = Zs + (size_t)(ty * 4) * DP4;
+        const float* yp = Ys + kc + tx * 4;
+        for (int dd = 0; dd < DP4; dd += 4) {
+          float4 z4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) z4[i] = *reinterpret_cast<const float4*>(zp + (size_t)i * DP4 + dd);
+#pragma unroll
+          for (int jd = 0; jd < 4; ++jd) {
+            float4 y4 = *reinterpret_cast<const float4*>(yp + (size_t)(dd + jd) * KP);
+            float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float zz = (jd == 0) ? z4[i].x : (jd == 1) ? z4[i].y : (jd == 2) ? z4[i].z : z4[i].w;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(zz, yy[j], acc[i][j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 o;
+          o.x = 2.f * (1.f - acc[i][0]);
+          o.y = 2.f * (1.f - acc[i][1]);
+          o.z = 2.f * (1.f - acc[i][2]);
+          o.w = 2.f * (1.f - acc[i][3]);
+          *reinterpret_cast<float4*>(Ls + (size_t)(ty * 4 + i) * LS + kc + tx * 4) = o;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- row epilogue: one warp per row, lanes over clusters
+    float cs[KQ];
+#pragma unroll
+    for (int qq = 0; qq < KQ; ++qq) cs[qq] = 0.f;
+    for (int r = warp; r < len; r += NWARP) {
+      const size_t row = (size_t)(cell0 + r);
+      float u[KQ], e[KQ], dist[KQ];
+      float s = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < KQ; ++qq) {
+        int k = lane + 32 * qq;
+        if (k < K) {
+          dist[qq] = Ls[(size_t)r * LS + k];
+          u[qq] = -dist[qq] / sig[k];
+          e[qq] = expf(u[qq]);
+        } else {
+          dist[qq] = 0.f;
+          u[qq] = 0.f;
+          e[qq] = 0.f;
+        }
+        s += e[qq];
+      }
+      s = warp_sum(s);
+      const float ls = logf(s);
+#pragma unroll
+      for (int qq = 0; qq < KQ; ++qq) {
+        int k = lane + 32 * qq;
+        if (k < K) {
+          float rv = e[qq] / s;  // R.each_row() /= sum(R, 0): no zero guard in the reference
+          a.U[row * K + k] = u[qq];
+          a.R[row * K + k] = rv;
+          cs[qq] += rv;
+          okd += rv * dist[qq];
+          if (rv > 0.f) oent += sig[k] * rv * (u[qq] - ls);
+        }
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < KQ; ++qq) {
+      int k = lane + 32 * qq;
+      if (k < KP) part[warp * KP + k] = cs[qq];
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += ASSIGN_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWARP; ++w) t += part[w * KP + k];
+      atomicAdd(a.rs_acc + k, t);
+      for (int c = 0; c < a.C; ++c) atomicAdd(a.O_acc + (size_t)a.tuple_levels[q * a.C + c] * K + k, t);
+    }
+  }
+  okd = warp_sum(okd);
+  oent = warp_sum(oent);
+  if (lane == 0) {
+    atomicAdd(a.obj_acc + 0, (double)okd);
+    atomicAdd(a.obj_acc + 1, (double)oent);
+  }
+}
+
+// E = sum(R,1) * Pr_b^T (harmony.cpp:149,226) and O from the accumulators.
+__global__ void k_assign_finalize(const float* __restrict__ O_acc, const float* __restrict__ rs_acc,
+                                  const float* __restrict__ Pr_b, float* __restrict__ O, float* __restrict__ E,
+                                  int B, int K) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < B * K) {
+    int b = idx / K, k = idx - b * K;
+    O[idx] = O_acc[idx];
+    E[idx] = rs_acc[k] * Pr_b[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// update-order plan (replaces the physical shuffles of harmony.cpp:272-291)
+// ------------------------------------------------------------------------------------------------
+// Injected order: for global position p, cell update_order[p] belongs to block min(p/cpb, nb-1).
+__global__ void k_plan_block_injected(const int64_t* __restrict__ update_order, int64_t N_global, int64_t cell_offset,
+                                      int64_t n_local, const int* __restrict__ inv_sort, uint32_t cpb, int nb,
+                                      int* __restrict__ blk_of, int* __restrict__ err_flag) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N_global;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = update_order[p];
+    if (g < 0 || g >= N_global) {
+      atomicExch(err_flag, 1);
+      continue;
+    }
+    int64_t l = g - cell_offset;
+    if (l < 0 || l >= n_local) continue;
+    int64_t b = p / cpb;
+    if (b > nb - 1) b = nb - 1;
+    blk_of[inv_sort[l]] = (int)b;
+  }
+}
+// Native order: position of global cell g is hb_permute(g) (a keyed bijection of [0, N)).
+__global__ void k_plan_block_native(int64_t N_global, int64_t cell_offset, int64_t n_local,
+                                    const int* __restrict__ sort_perm, uint32_t cpb, int nb, int half_bits,
+                                    uint64_t key, int* __restrict__ blk_of) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n_local;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t g = (uint64_t)(cell_offset + sort_perm[s]);
+    uint64_t pos = hb_permute(g, (uint64_t)N_global, half_bits, key);
+    uint64_t b = pos / cpb;
+    if (b > (uint64_t)(nb - 1)) b = nb - 1;
+    blk_of[s] = (int)b;
+  }
+}
+// One warp per chunk (<= chunk cells of one tuple): H[blk][chunk] = #cells of the chunk in block blk.
+__global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restrict__ chunk_start, int nchunks,
+                            int nb, int* __restrict__ H) {
+  extern __shared__ int sh[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cnt = sh + warp * nb;
+  int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= nchunks) return;
+  for (int j = lane; j < nb; j += 32) cnt[j] = 0;
+  __syncwarp();
+  int s0 = chunk_start[c], s1 = chunk_start[c + 1];
+  for (int s = s0 + lane; s < s1; s += 32) atomicAdd(cnt + blk_of[s], 1);
+  __syncwarp();
+  for (int j = lane; j < nb; j += 32) H[(size_t)j * nchunks + c] = cnt[j];
+}
+// Single-CTA exclusive scan of an int array (in place), total written to *total.
+__global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data, int64_t n, int* __restrict__ total) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t lo = (int64_t)tid * per, hi = (lo + per < n) ? lo + per : n;
+  int s = 0;
+  for (int64_t i = lo; i < hi; ++i) s += data[i];
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+    int inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += t;
+    }
+    wsum[lane] = inc2 - v;
+    if (lane == 31) carry = inc2;
+  }
+  __syncthreads();
+  int base = wsum[warp] + incl - s;
+  for (int64_t i = lo; i < hi; ++i) {
+    int v = data[i];
+    data[i] = base;
+    base += v;
+  }
+  if (tid == 0 && total) *total = carry;
+}
+// Stable scatter: order[offset(blk, chunk) + rank] = cell, cells of a chunk visited in ascending order.
+__global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __restrict__ chunk_start, int nchunks,
+                               int nb, const int* __restrict__ Hoff, int* __restrict__ order) {
+  extern __shared__ int sh[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cur = sh + warp * nb;
+  int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= nchunks) return;
+  for (int j = lane; j < nb; j += 32) cur[j] = Hoff[(size_t)j * nchunks + c];
+  __syncwarp();
+  int s0 = chunk_start[c], s1 = chunk_start[c + 1];
+  for (int base = s0; base < s1; base += 32) {
+    int s = base + lane;
+    bool act = s < s1;
+    int b = act ? blk_of[s] : -1 - lane;  // inactive lanes get unique keys
+    unsigned m = __match_any_sync(0xffffffffu, b);
+    int rank = __popc(m & ((1u << lane) - 1u));
+    int leader = __ffs(m) - 1;
+    int start = 0;
+    if (act && lane == leader) {
+      start = cur[b];
+      cur[b] = start + __popc(m);
+    }
+    start = __shfl_sync(0xffffffffu, start, leader);
+    if (act) order[start + rank] = s;
+    __syncwarp();
+  }
+}
+// Segment (block, tuple) boundaries and tile counts: seg s = blk*J + q.
+//   seg_start[s] = Hoff[blk][first chunk of q];  tiles[s] = ceil(len / TM)   (scanned afterwards)
+__global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restrict__ tuple_chunk0, int nchunks,
+                                int nb, int J, int n_local, int* __restrict__ seg_start, int* __restrict__ tile_base) {
+  int S = nb * J;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x) {
+    int v;
+    if (s == S) {
+      v = n_local;
+    } else {
+      int blk = s / J, q = s - blk * J;
+      int c = tuple_chunk0[q];  // first chunk of tuple q (== nchunks when q has no later chunks)
+      // empty tuples cannot occur (every tuple has >= 1 cell), so c < nchunks
+      v = Hoff[(size_t)blk * nchunks + c];
+    }
+    seg_start[s] = v;
+  }
+}
+__global__ void k_plan_tilecount(const int* __restrict__ seg_start, int S, int* __restrict__ tile_base) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x) {
+    int len = (s < S) ? seg_start[s + 1] - seg_start[s] : 0;
+    tile_base[s] = (len + TM - 1) / TM;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// update_R block step (harmony.cpp:293-332)
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+  const float* U;
+  float* R;
+  const int* order;         // [n] cells sorted by (block, tuple, cell)
+  const int* seg_start;     // [nb*J + 1]
+  const int* tile_base;     // [nb*J + 1] exclusive scan of tiles per segment
+  const int* tuple_levels;  // [J][C]
+  const float* sigma;
+  const float* P;           // [B][K] penalty table of this step
+  float* acc_O;             // [B][K] column sums per level (rem_j or add_j)
+  float* acc_rs;            // [K]
+  double* obj_acc;          // [2]
+  int blk, J, K, C, KP;
+};
+
+// tile -> (segment, first position, length)
+__device__ __forceinline__ bool locate_tile(const StepArgs& a, int t, int* sh_info) {
+  // sh_info: [0] seg, [1] p0, [2] len, [3] valid
+  if (threadIdx.x == 0) {
+    int s_lo = a.blk * a.J, s_hi = (a.blk + 1) * a.J;
+    int t0 = a.tile_base[s_lo], t1 = a.tile_base[s_hi];
+    int tt = t0 + t;
+    if (tt >= t1) {
+      sh_info[3] = 0;
+    } else {
+      int lo = s_lo, hi = s_hi;  // find the last seg with tile_base[seg] <= tt
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (a.tile_base[mid] <= tt) lo = mid; else hi = mid;
+      }
+      int p0 = a.seg_start[lo] + (tt - a.tile_base[lo]) * TM;
+      int len = a.seg_start[lo + 1] - p0;
+      sh_info[0] = lo;
+      sh_info[1] = p0;
+      sh_info[2] = len < TM ? len : TM;
+      sh_info[3] = 1;
+    }
+  }
+  __syncthreads();
+  return sh_info[3] != 0;
+}
+
+// Step 1 (:312-313): column sums of the block's current R, per level  ->  acc_O / acc_rs
+template <int KQ>
+__global__ void __launch_bounds__(ROW_THREADS) k_block_colsum(StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int info[4];
+  const int K = a.K, KP = a.KP;
+  float* part = smem;  // [NWARP][KP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = blockIdx.x;; t += gridDim.x) {
+    __syncthreads();
+    if (!locate_tile(a, t, info)) break;
+    const int seg = info[0], p0 = info[1], len = info[2];
+    const int q = seg - a.blk * a.J;
+    float cs[KQ];
+#pragma unroll
+    for (int qq = 0; qq < KQ; ++qq) cs[qq] = 0.f;
+    for (int r = warp; r < len; r += NWARP) {
+      const size_t row = (size_t)a.order[p0 + r];
+#pragma unroll
+      for (int qq = 0; qq < KQ; ++qq) {
+        int k = lane + 32 * qq;
+        if (k < K) cs[qq] += a.R[row * K + k];
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < KQ; ++qq) {
+      int k = lane + 32 * qq;
+      if (k < KP) part[warp * KP + k] = cs[qq];
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += ROW_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWARP; ++w) s += part[w * KP + k];
+      atomicAdd(a.acc_rs + k, s);
+      for (int c = 0; c < a.C; ++c) atomicAdd(a.acc_O + (size_t)a.tuple_levels[q * a.C + c] * K + k, s);
+    }
+  }
+}
+
+// Finish step j-1 and start step j on the K x B tables:
+//   O += add_prev; E += rs_add_prev*Pr_b        (:329-330 of the previous block)
+//   O -= rem;      E -= rs_rem*Pr_b             (:312-313 of this block)
+//   P = ((2E+1)/(O+E+1))^theta                  (:322, harmony_pow utils.cpp:84-90)
+// add_prev / rem may be null (first step of a round / finalisation after the last step).
+__global__ void k_step_prepare(float* __restrict__ O, float* __restrict__ E, const float* __restrict__ add_O,
+                               const float* __restrict__ add_rs, const float* __restrict__ rem_O,
+                               const float* __restrict__ rem_rs, const float* __restrict__ Pr_b,
+                               const float* __restrict__ theta, float* __restrict__ P, int B, int K) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * K) return;
+  int b = idx / K, k = idx - b * K;
+  float o = O[idx], e = E[idx];
+  if (add_O) {
+    e += add_rs[k] * Pr_b[b];
+    o += add_O[idx];
+  }
+  if (rem_O) {
+    e -= rem_rs[k] * Pr_b[b];
+    o -= rem_O[idx];
+  }
+  O[idx] = o;
+  E[idx] = e;
+  if (P) P[idx] = powf(((2.f * e) + 1.f) / (o + e + 1.f), theta[b]);
+}
+
+// Step 2+3 (:318-330): R = L1norm(exp(U) * sum_c P[level_c]), column sums of the new R -> acc_O/acc_rs,
+// objective partials of the new R.
+template <int KQ>
+__global__ void __launch_bounds__(ROW_THREADS) k_block_update(StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int info[4];
+  const int K = a.K, KP = a.KP;
+  float* part = smem;             // [NWARP][KP]
+  float* Psum = part + NWARP * KP;  // [KP]
+  float* lP = Psum + KP;          // [KP]
+  float* sig = lP + KP;           // [KP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < KP; k += ROW_THREADS) sig[k] = (k < K) ? a.sigma[k] : 1.f;
+  float okd = 0.f, oent = 0.f;
+  for (int t = blockIdx.x;; t += gridDim.x) {
+    __syncthreads();
+    if (!locate_tile(a, t, info)) break;
+    const int seg = info[0], p0 = info[1], len = info[2];
+    const int q = seg - a.blk * a.J;
+    for (int k = tid; k < K; k += ROW_THREADS) {
+      float s = 0.f;
+      for (int c = 0; c < a.C; ++c) s += a.P[(size_t)a.tuple_levels[q * a.C + c] * K + k];
+      Psum[k] = s;
+      lP[k] = logf(s);
+    }
+    __syncthreads();
+    float cs[KQ];
+#pragma unroll
+    for (int qq = 0; qq < KQ; ++qq) cs[qq] = 0.f;
+    for (int r = warp; r < len; r += NWARP) {
+      const size_t row = (size_t)a.order[p0 + r];
+      float u[KQ], e[KQ];
+      float s = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < KQ; ++qq) {
+        int k = lane + 32 * qq;
+        if (k < K) {
+          u[qq] = ld_stream(a.U + row * K + k);
+          e[qq] = expf(u[qq]) * Psum[k];
+        } else {
+          u[qq] = 0.f;
+          e[qq] = 0.f;
+        }
+        s += fabsf(e[qq]);
+      }
+      s = warp_sum(s);
+      const float sdiv = (s == 0.f) ? 1.f : s;  // arma::normalise(.., 1, 0): zero norm divides by 1
+      const float ls = logf(sdiv);
+#pragma unroll
+      for (int qq = 0; qq < KQ; ++qq) {
+        int k = lane + 32 * qq;
+        if (k < K) {
+          float rv = e[qq] / sdiv;
+          st_stream(a.R + row * K + k, rv);
+          cs[qq] += rv;
+          okd += rv * (-sig[k] * u[qq]);
+          if (rv > 0.f) oent += sig[k] * rv * (u[qq] + lP[k] - ls);
+        }
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < KQ; ++qq) {
+      int k = lane + 32 * qq;
+      if (k < KP) part[warp * KP + k] = cs[qq];
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += ROW_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NWARP; ++w) s += part[w * KP + k];
+      atomicAdd(a.acc_rs + k, s);
+      for (int c = 0; c < a.C; ++c) atomicAdd(a.acc_O + (size_t)a.tuple_levels[q * a.C + c] * K + k, s);
+    }
+  }
+  okd = warp_sum(okd);
+  oent = warp_sum(oent);
+  if (lane == 0) {
+    atomicAdd(a.obj_acc + 0, (double)okd);
+    atomicAdd(a.obj_acc + 1, (double)oent);
+  }
+}
+
+// compute_objective (harmony.cpp:158-170) once the per-cell sums are known:
+//   cross = sum_kb sigma_k theta_b log((O+E+1)/(2E+1)) O_kb   (== the reference's N-pass, SURVEY §8a')
+// Appends (total, dist, entropy, cross) * 2000/N to the device trace at slot `slot` and clears obj_acc.
+__global__ void __launch_bounds__(256) k_objective_finalize(const float* __restrict__ O, const float* __restrict__ E,
+                                                            const float* __restrict__ theta,
+                                                            const float* __restrict__ sigma, double* obj_acc,
+                                                            float* __restrict__ trace, int slot, int B, int K,
+                                                            double N_global, double cross_scale) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int idx = threadIdx.x; idx < B * K; idx += blockDim.x) {
+    int b = idx / K, k = idx - b * K;
+    float o = O[idx], e = E[idx];
+    float l = theta[b] * logf((o + e + 1.f) / ((2.f * e) + 1.f));
+    acc += (double)(sigma[k] * l) * (double)o;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double cross = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) cross += red[w];
+    cross *= cross_scale;  // 1 normally; the cross term is replicated, not sharded
+    const float norm_const = 2000.f / (float)N_global;
+    float kd = (float)obj_acc[0], ent = (float)obj_acc[1], cr = (float)cross;
+    trace[4 * slot + 0] = (kd + ent + cr) * norm_const;
+    trace[4 * slot + 1] = kd * norm_const;
+    trace[4 * slot + 2] = ent * norm_const;
+    trace[4 * slot + 3] = cr * norm_const;
+    obj_acc[0] = 0.0;
+    obj_acc[1] = 0.0;
+  }
+}
+
+// Standalone per-cell objective sums from the stored R and U (for hb_compute_objective).
+__global__ void __launch_bounds__(ROW_THREADS) k_objective_cells(const float* __restrict__ R, const float* __restrict__ U,
+                                                                const float* __restrict__ sigma, int64_t n, int K,
+                                                                double* obj_acc) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float okd = 0.f, oent = 0.f;
+  for (int64_t r = w; r < n; r += nw) {
+    for (int k = lane; k < K; k += 32) {
+      float rv = R[r * K + k], u = U[r * K + k], sg = sigma[k];
+      okd += rv * (-sg * u);
+      if (rv > 0.f) oent += sg * rv * logf(rv);
+    }
+  }
+  okd = warp_sum(okd);
+  oent = warp_sum(oent);
+  if (lane == 0) {
+    atomicAdd(obj_acc + 0, (double)okd);
+    atomicAdd(obj_acc + 1, (double)oent);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: ridge sufficient statistics (harmony.cpp:561-567, 592-609 for all clusters at once)
+//   S[q][k][0..d-1] = sum_{i in tuple q} R_ik * Zo_i      S[q][k][d] = sum_{i in tuple q} R_ik
+// Output-stationary fp32 register tiling: thread (ty, tx) owns clusters ty*8..+7 x columns tx*4..+3.
+// ------------------------------------------------------------------------------------------------
+struct StatsArgs {
+  const float* R;
+  const float* Zo;
+  const int* tile_cell0;
+  const int* tile_len;
+  const int* tile_tuple;
+  float* S;  // [J][K][d+1]
+  int ntiles, d, K, KS;  // KS = clusters per K-slice (blockIdx.y)
+  int tiles_per_cta;
+};
+
+__global__ void k_ridge_stats(StatsArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int d = a.d, K = a.K, D1 = d + 1;
+  const int k0 = blockIdx.y * a.KS;
+  const int ks = (K - k0 < a.KS) ? K - k0 : a.KS;  // clusters in this slice
+  const int KSP = (a.KS + 7) & ~7;                   // padded slice width (multiple of 8)
+  const int DP = (D1 + 3) & ~3;
+  float* Rs = smem;                      // [TM][KSP]
+  float* Zs = Rs + (size_t)TM * KSP;     // [TM][DP]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  int cur_q = -1;
+  const int t_begin = blockIdx.x * a.tiles_per_cta;
+  const int t_end = (t_begin + a.tiles_per_cta < a.ntiles) ? t_begin + a.tiles_per_cta : a.ntiles;
+
+  auto flush = [&](int q) {
+    if (q < 0) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int k = ty * 8 + i;
+      if (k < ks) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int c = tx * 4 + j;
+          if (c < D1) atomicAdd(a.S + ((size_t)q * K + k0 + k) * D1 + c, acc[i][j]);
+          acc[i][j] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      }
+    }
+  };
+
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int cell0 = a.tile_cell0[tile], len = a.tile_len[tile], q = a.tile_tuple[tile];
+    if (q != cur_q) {
+      flush(cur_q);
+      cur_q = q;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < TM * KSP; idx += nthr) {
+      int r = idx / KSP, k = idx - r * KSP;
+      Rs[idx] = (r < len && k < ks) ? ld_stream(a.R + (size_t)(cell0 + r) * K + k0 + k) : 0.f;
+    }
+    for (int idx = tid; idx < TM * DP; idx += nthr) {
+      int r = idx / DP, c = idx - r * DP;
+      float v = 0.f;
+      if (r < len) v = (c < d) ? ld_stream(a.Zo + (size_t)(cell0 + r) * d + c) : ((c == d) ? 1.f : 0.f);
+      Zs[idx] = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < TM; ++r) {
+      float4 r0 = *reinterpret_cast<const float4*>(Rs + (size_t)r * KSP + ty * 8);
+      float4 r1 = *reinterpret_cast<const float4*>(Rs + (size_t)r * KSP + ty * 8 + 4);
+      float4 z = *reinterpret_cast<const float4*>(Zs + (size_t)r * DP + tx * 4);
+      float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(rr[i], zz[j], acc[i][j]);
+    }
+  }
+  flush(cur_q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: per-cluster level filter + ridge solve (harmony.cpp:358-410, 561-611, 633); one CTA per cluster.
+// Produces the per-tuple correction matrices V[q][k][:] = sum over the tuple's kept levels of W_k[level],
+// the new centroid Y[k] (L2-normalised) and Wfull[k] = W_k expanded to B+1 rows (row 0 zeroed).
+// ------------------------------------------------------------------------------------------------
+struct SolveArgs {
+  const float* S;             // [J][K][d+1]
+  const float* O;             // [B][K]
+  const float* E;             // [B][K]
+  const float* N_b;           // [B]
+  const float* lambda;        // [B+1] or null (estimation)
+  const int* tuple_levels;    // [J][C]
+  const int* cov_of;          // [B]
+  float* Y;                   // [K][d]
+  float* V;                   // [J][K][d]
+  float* Wfull;               // [K][B+1][d]
+  int* skipped;               // [K]
+  float* scratch;             // [K][ 2*M*M + M*d ]  (G | inv | s),  M = B+1
+  int* iscratch;              // [K][ 2*B + J ]      (pos | keep | part)
+  int* err_flag;
+  int J, K, B, C, d;
+  float alpha, cutoff;
+};
+
+__global__ void __launch_bounds__(256) k_ridge_solve(SolveArgs a) {
+  const int k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int J = a.J, K = a.K, B = a.B, C = a.C, d = a.d, D1 = d + 1, M = B + 1;
+  __shared__ int sh_m;       // kept levels + 1
+  __shared__ float sh_f[4];
+  __shared__ int sh_piv;
+  float* G = a.scratch + (size_t)k * (2 * (size_t)M * M + (size_t)M * d);
+  float* inv = G + (size_t)M * M;
+  float* sv = inv + (size_t)M * M;  // [m][d]
+  int* pos = a.iscratch + (size_t)k * (2 * B + J);  // level -> kept index (or -1)
+  int* keep = pos + B;                              // kept index -> level
+  int* part = keep + B;                             // tuple participates?
+
+  // ---- level filter (:358-410)
+  extern __shared__ int sh_i[];  // [B] over-cutoff flags, [C] levels above the cutoff per covariate
+  int* over = sh_i;
+  int* cov_levels = sh_i + B;
+  for (int c = tid; c < C; c += nt) cov_levels[c] = 0;
+  __syncthreads();
+  for (int b = tid; b < B; b += nt) {
+    int ov = ((a.O[(size_t)b * K + k] / a.N_b[b]) > a.cutoff) ? 1 : 0;
+    over[b] = ov;
+    if (ov) atomicAdd(&cov_levels[a.cov_of[b]], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int nkeep = 0;
+    for (int b = 0; b < B; ++b) {
+      if (over[b] && cov_levels[a.cov_of[b]] > 1) {
+        pos[b] = nkeep;
+        keep[nkeep] = b;
+        nkeep++;
+      } else {
+        pos[b] = -1;
+      }
+    }
+    sh_m = nkeep + 1;
+    a.skipped[k] = (nkeep == 0) ? 1 : 0;
+  }
+  __syncthreads();
+  const int m = sh_m;
+  float* Wk = a.Wfull + (size_t)k * M * d;
+  if (m == 1) {  // no active covariate (:449-452): cluster untouched, Y[k] keeps its value
+    for (int idx = tid; idx < J * d; idx += nt) {
+      int q = idx / d, c = idx - q * d;
+      a.V[((size_t)q * K + k) * d + c] = 0.f;
+    }
+    for (int idx = tid; idx < M * d; idx += nt) Wk[idx] = 0.f;
+    return;
+  }
+  // ---- participating tuples, zero G and s
+  for (int q = tid; q < J; q += nt) {
+    int p = 0;
+    for (int c = 0; c < C; ++c) p |= (pos[a.tuple_levels[q * C + c]] >= 0);
+    part[q] = p;
+  }
+  for (int idx = tid; idx < m * m; idx += nt) G[idx] = 0.f;
+  __syncthreads();
+  // ---- G = Phi* diag(R_k) Phi*^T (:561-567) folded from the per-tuple sums n_kq = S[q][k][d]
+  for (int q = tid; q < J; q += nt) {
+    if (!part[q]) continue;
+    float nq = a.S[((size_t)q * K + k) * D1 + d];
+    atomicAdd(&G[0], nq);
+    for (int c1 = 0; c1 < C; ++c1) {
+      int p1 = pos[a.tuple_levels[q * C + c1]];
+      if (p1 < 0) continue;
+      atomicAdd(&G[(size_t)(p1 + 1) * m], nq);  // row 0
+      atomicAdd(&G[(size_t)(p1 + 1)], nq);      // col 0
+      for (int c2 = 0; c2 < C; ++c2) {
+        int p2 = pos[a.tuple_levels[q * C + c2]];
+        if (p2 < 0) continue;
+        atomicAdd(&G[(size_t)(p2 + 1) * m + (p1 + 1)], nq);
+      }
+    }
+  }
+  // ---- s = Phi* diag(R_k) Zo^T: thread per embedding column, serial over tuples (no atomics)
+  for (int c = tid; c < d; c += nt) {
+    for (int r = 0; r < m; ++r) sv[(size_t)r * d + c] = 0.f;
+    for (int q = 0; q < J; ++q) {
+      if (!part[q]) continue;
+      float v = a.S[((size_t)q * K + k) * D1 + c];
+      sv[c] += v;
+      for (int c1 = 0; c1 < C; ++c1) {
+        int p1 = pos[a.tuple_levels[q * C + c1]];
+        if (p1 >= 0) sv[(size_t)(p1 + 1) * d + c] += v;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- + diag(lambda): lambda_0 = 0, lambda_b = alpha*E_kb (find_lambda_cpp) or the fixed vector
+  for (int j = tid; j < m - 1; j += nt) {
+    int b = keep[j];
+    float lam = a.lambda ? a.lambda[b + 1] : a.E[(size_t)b * K + k] * a.alpha;
+    G[(size_t)(j + 1) * m + (j + 1)] += lam;
+  }
+  if (tid == 0 && a.lambda) G[0] += a.lambda[0];
+  __syncthreads();
+  // ---- inverse
+  if (C == 1) {
+    // arrowhead closed form (:575-586)
+    if (tid == 0) {
+      float accum = 0.f;
+      for (int j = 1; j < m; ++j) {
+        float ac = -G[(size_t)j * m];
+        float bj = 1.f / G[(size_t)j * m + j];
+        accum += (ac * ac) * bj;
+      }
+      sh_f[0] = G[0] - accum;  // u
+    }
+    __syncthreads();
+    const float u = sh_f[0];
+    for (int idx = tid; idx < m * m; idx += nt) {
+      int r = idx % m, c = idx / m;
+      float acr = (r == 0) ? 1.f : (-G[(size_t)r * m]) * (1.f / G[(size_t)r * m + r]);
+      float acc_ = (c == 0) ? 1.f : (-G[(size_t)c * m]) * (1.f / G[(size_t)c * m + c]);
+      float v = (1.f / u) * (acr * acc_);
+      if (r == c && r > 0) v += 1.f / G[(size_t)r * m + r];
+      inv[idx] = v;
+    }
+    __syncthreads();
+  } else {
+    // Gauss-Jordan with partial pivoting (arma::inv -> getrf/getri, :573); column-major m x m
+    for (int idx = tid; idx < m * m; idx += nt) inv[idx] = ((idx % m) == (idx / m)) ? 1.f : 0.f;
+    __syncthreads();
+    for (int c = 0; c < m; ++c) {
+      if (tid == 0) {
+        int piv = c;
+        float best = fabsf(G[c + (size_t)c * m]);
+        for (int r = c + 1; r < m; ++r) {
+          float v = fabsf(G[r + (size_t)c * m]);
+          if (v > best) {
+            best = v;
+            piv = r;
+          }
+        }
+        sh_piv = piv;
+        if (!(best > 0.f) || !isfinite(best)) atomicExch(a.err_flag, 2);
+      }
+      __syncthreads();
+      const int piv = sh_piv;
+      if (piv != c) {
+        for (int j = tid; j < m; j += nt) {
+          float t = G[c + (size_t)j * m];
+          G[c + (size_t)j * m] = G[piv + (size_t)j * m];
+          G[piv + (size_t)j * m] = t;
+          t = inv[c + (size_t)j * m];
+          inv[c + (size_t)j * m] = inv[piv + (size_t)j * m];
+          inv[piv + (size_t)j * m] = t;
+        }
+        __syncthreads();
+      }
+      if (tid == 0) sh_f[1] = G[c + (size_t)c * m];
+      __syncthreads();
+      const float p = sh_f[1];
+      for (int j = tid; j < m; j += nt) {
+        G[c + (size_t)j * m] /= p;
+        inv[c + (size_t)j * m] /= p;
+      }
+      __syncthreads();
+      // eliminate column c from every other row: thread per (row, col) pair
+      // first snapshot the factors (column c of G) into sv's tail? use registers per row instead:
+      for (int idx = tid; idx < m * m; idx += nt) {
+        int r = idx % m, j = idx / m;
+        if (r == c) continue;
+        float f = G[r + (size_t)c * m];
+        if (j == c) continue;  // column c itself is cleared afterwards
+        G[r + (size_t)j * m] -= f * G[c + (size_t)j * m];
+      }
+      for (int idx = tid; idx < m * m; idx += nt) {
+        int r = idx % m, j = idx / m;
+        if (r == c) continue;
+        float f = G[r + (size_t)c * m];
+        inv[r + (size_t)j * m] -= f * inv[c + (size_t)j * m];
+      }
+      __syncthreads();
+      for (int r = tid; r < m; r += nt)
+        if (r != c) G[r + (size_t)c * m] = 0.f;
+      __syncthreads();
+    }
+  }
+  // ---- W = inv * s  (:599-609), Y[k] = W[0] (:610), W[0] = 0 (:611)
+  for (int idx = tid; idx < M * d; idx += nt) Wk[idx] = 0.f;
+  __syncthreads();
+  for (int idx = tid; idx < m * d; idx += nt) {
+    int r = idx / d, c = idx - r * d;
+    float w = 0.f;
+    for (int j = 0; j < m; ++j) w += inv[r + (size_t)j * m] * sv[(size_t)j * d + c];
+    if (r == 0)
+      a.Y[(size_t)k * d + c] = w;
+    else
+      Wk[(size_t)(keep[r - 1] + 1) * d + c] = w;
+  }
+  __syncthreads();
+  // ---- Y = normalise(Y, 2, 0) (:633) for this column
+  if (tid < 32) {
+    float s = 0.f;
+    for (int c = tid; c < d; c += 32) {
+      float v = a.Y[(size_t)k * d + c];
+      s += v * v;
+    }
+    s = warp_sum(s);
+    float nrm = sqrtf(s);
+    if (nrm == 0.f) nrm = 1.f;
+    for (int c = tid; c < d; c += 32) a.Y[(size_t)k * d + c] /= nrm;
+  }
+  // ---- V[q][k] = sum of the kept levels' betas of tuple q (0 for tuples that do not take part)
+  for (int idx = tid; idx < J * d; idx += nt) {
+    int q = idx / d, c = idx - q * d;
+    float v = 0.f;
+    if (part[q])
+      for (int c1 = 0; c1 < C; ++c1) {
+        int b = a.tuple_levels[q * C + c1];
+        if (pos[b] >= 0) v += Wk[(size_t)(b + 1) * d + c];
+      }
+    a.V[((size_t)q * K + k) * d + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: apply (harmony.cpp:347 + :615 for all clusters): Zc_i = Zo_i - sum_k R_ik V[q(i)][k][:]
+// thread (ty, tx) owns cells ty*4..+3 x columns tx*4..+3 of a TM-cell tile.
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const float* R;
+  const float* Zo;
+  const float* V;  // [J][K][d]
+  float* Zc;
+  const int* tile_cell0;
+  const int* tile_len;
+  const int* tile_tuple;
+  int ntiles, d, K, tiles_per_cta;
+};
+
+__global__ void k_ridge_apply(ApplyArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int d = a.d, K = a.K;
+  const int DP = (d + 3) & ~3, KP4 = (K + 3) & ~3;
+  float* Vs = smem;                      // [KP4][DP]  (rows >= K and columns >= d are zero)
+  float* Rs = Vs + (size_t)KP4 * DP;     // [TM][KP4]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * blockDim.x + tx, nthr = blockDim.x * blockDim.y;
+  int cur_q = -1;
+  const int t_begin = blockIdx.x * a.tiles_per_cta;
+  const int t_end = (t_begin + a.tiles_per_cta < a.ntiles) ? t_begin + a.tiles_per_cta : a.ntiles;
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int cell0 = a.tile_cell0[tile], len = a.tile_len[tile], q = a.tile_tuple[tile];
+    __syncthreads();
+    if (q != cur_q) {
+      for (int idx = tid; idx < KP4 * DP; idx += nthr) {
+        int k = idx / DP, c = idx - k * DP;
+        Vs[idx] = (c < d && k < K) ? a.V[((size_t)q * K + k) * d + c] : 0.f;
+      }
+      cur_q = q;
+    }
+    for (int idx = tid; idx < TM * KP4; idx += nthr) {
+      int r = idx / KP4, k = idx - r * KP4;
+      Rs[idx] = (r < len && k < K) ? ld_stream(a.R + (size_t)(cell0 + r) * K + k) : 0.f;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* rp = Rs + (size_t)(ty * 4) * KP4;
+    const float* vp = Vs + tx * 4;
+    for (int k = 0; k < KP4; k += 4) {
+      float4 r4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r4[i] = *reinterpret_cast<const float4*>(rp + (size_t)i * KP4 + k);
+#pragma unroll
+      for (int jk = 0; jk < 4; ++jk) {
+        float4 v4 = *reinterpret_cast<const float4*>(vp + (size_t)(k + jk) * DP);
+        float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float rr = (jk == 0) ? r4[i].x : (jk == 1) ? r4[i].y : (jk == 2) ? r4[i].z : r4[i].w;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(rr, vv[j], acc[i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = ty * 4 + i;
+      if (r < len) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int c = tx * 4 + j;
+          if (c < d) {
+            size_t g = (size_t)(cell0 + r) * d + c;
+            a.Zc[g] = a.Zo[g] - acc[i][j];
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace hb

@@ -140,4 +140,4 @@ def RunHarmony(data_mat, meta_data, vars_use=None, theta=None, sigma=0.1, lambda
         HarmonyConvergencePlot(obj)
     if return_object:
         return obj
-    return obj.getZcorr().T.copy() if np.asarray(data_mat).shape[0] != a["Z"].shape[0] else obj.getZcorr()
+    return np.ascontiguousarray(obj.getZcorr().T)   # t(harmonyObj$getZcorr()), R/ui.R:292-295: cells x PCs

@@ -1,0 +1,199 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the ``harmony`` class) against the CPU oracle on
+the same inputs, with the k-means centroids and the per-round update orders injected into both
+(parity is only definable that way).
+
+Tolerances (BASELINE.json north_star): corrected embedding within 1e-4 rel-L2 of the reference-order
+fp32 oracle; hard cluster index argmax_k R identical except for cells whose top-2 gap is inside the
+fp32 noise band (< 1e-5).  We additionally require the GPU to be no further from the fp64 oracle than
+2x the fp32 oracle is (+ a small floor).
+"""
+import numpy as np
+import pytest
+
+from harmony_b200 import harmony_options, prepare_inputs
+from helpers import load_cell_lines, load_pbmc, make_perms, make_Y0, rel_l2, run_oracle, synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL_Z = 1e-4
+TIE_BAND = 1e-5
+
+
+def run_gpu(a, Y0, n_iter, perms):
+    from harmony_b200.harmony import harmony
+    g = harmony()
+    g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], a["max_iter_kmeans"],
+            a["epsilon_kmeans"], a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"],
+            a["batch_proportion_cutoff"], False)
+    g.init_cluster_cpp(Y0)
+    iters = 0
+    for it in range(n_iter):
+        assert g.cluster_cpp(perms[it]) == 0
+        g.moe_correct_ridge_cpp()
+        iters += 1
+        if g.check_convergence(1):
+            break
+    return g, iters
+
+
+def argmax_mismatch_outside_band(Rg, Ro):
+    """#cells whose hard assignment differs although the oracle's top-2 gap exceeds the noise band."""
+    ag, ao = Rg.argmax(axis=1), Ro.argmax(axis=1)
+    part = np.partition(Ro, -2, axis=1)
+    gap = part[:, -1] - part[:, -2]
+    bad = (ag != ao) & (gap > TIE_BAND)
+    return int(bad.sum()), int((ag != ao).sum())
+
+
+def compare(g, o32, o64, label):
+    Zg, Z32, Z64 = g.getZcorr().T, o32.get("Z_corr"), o64.get("Z_corr")
+    Rg, R32 = g.R.T, o32.get("R")
+    e_g32, e_g64, e_3264 = rel_l2(Zg, Z32), rel_l2(Zg, Z64), rel_l2(Z32, Z64)
+    bad, anydiff = argmax_mismatch_outside_band(Rg, R32)
+    dR = float(np.abs(Rg - R32).max())
+    dY = float(np.abs(g.Y.T - o32.get("Y")).max())
+    dO = float(np.abs(g.O.T - o32.get("O")).max() / max(1.0, np.abs(o32.get("O")).max()))
+    print(f"[{label}] relL2(Z gpu,o32)={e_g32:.2e} (gpu,o64)={e_g64:.2e} (o32,o64)={e_3264:.2e} "
+          f"max|dR|={dR:.2e} max|dY|={dY:.2e} rel|dO|={dO:.2e} argmax diff={anydiff} outside band={bad}")
+    assert np.all(np.isfinite(Zg))
+    assert e_g32 <= TOL_Z
+    assert e_g64 <= 2 * e_3264 + 2e-5
+    assert bad == 0
+    assert dR <= 5e-4
+    np.testing.assert_allclose(Rg.sum(axis=1), 1.0, atol=1e-5)
+    # traces: same lengths, values within fp32 summation noise of the fp64 truth
+    for name in ("objective_kmeans", "objective_harmony", "objective_kmeans_dist", "objective_kmeans_entropy",
+                 "objective_kmeans_cross"):
+        tg, t64 = getattr(g, name), o64.trace(name)
+        assert len(tg) == len(t64), name
+        np.testing.assert_allclose(tg, t64, rtol=2e-4, atol=2e-4, err_msg=name)
+    assert list(g.kmeans_rounds) == [int(x) for x in o32.trace("kmeans_rounds")]
+
+
+CASES = {
+    # config 1 of BASELINE.json: cell_lines_small, 1 covariate, K=5
+    "cell_lines_small_K5": lambda: (load_cell_lines(True), "dataset", dict(nclust=5)),
+    # test_integration.R:5-7
+    "cell_lines_small_K50_T10": lambda: (load_cell_lines(True), "dataset",
+                                         dict(theta=1, nclust=50, options=harmony_options(max_iter_cluster=10))),
+    # test_two_variable.R:5-11 (arma::inv branch)
+    "cell_lines_2cov_K50": lambda: (load_cell_lines(False), ["cell_type", "dataset"],
+                                    dict(theta=[1, 1], nclust=50, options=harmony_options(max_iter_cluster=10))),
+    "cell_lines_1cov_default": lambda: (load_cell_lines(False), "dataset", dict()),
+    # config 2 of BASELINE.json: pbmc_stim, 50 PCs, covariate stim, K=50
+    "pbmc_stim_K50": lambda: (load_pbmc(), "stim", dict(nclust=50)),
+    "synthetic_3cov_nested": lambda: (synthetic(6000, 30, [4, 12, 3], seed=3), ["cov0", "cov1", "cov2"],
+                                      dict(nclust=40, theta=[2, 1, 0.5])),
+    "synthetic_fixed_lambda": lambda: (synthetic(5000, 16, [5], seed=4), "cov0", dict(nclust=24, lambda_=1.0)),
+    "synthetic_theta0_sigma_vec": lambda: (synthetic(4000, 10, [3], seed=5), "cov0",
+                                           dict(nclust=7, theta=0, sigma=np.linspace(0.08, 0.15, 7))),
+    "synthetic_blocksize_odd": lambda: (synthetic(3001, 9, [2, 4], seed=6, nested=False), ["cov0", "cov1"],
+                                        dict(nclust=33, options=harmony_options(block_size=0.07, max_iter_cluster=6))),
+    "synthetic_K100_d50": lambda: (synthetic(20000, 50, [20], n_types=30, seed=7), "cov0", dict(nclust=100)),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_parity_full_run(case):
+    (Z, meta), vars_use, kw = CASES[case]()
+    a = prepare_inputs(Z, meta, vars_use, early_stop=False, **kw)
+    N, T = Z.shape[0], a["max_iter_kmeans"]
+    n_iter = 3
+    Y0 = make_Y0(Z, a["K"], 17)
+    perms = make_perms(N, n_iter * T, 23).reshape(n_iter, T, N)
+    o32, _, _ = run_oracle(a, Y0, n_iter, perms=perms)
+    o64, _, _ = run_oracle(a, Y0, n_iter, perms=perms, double=True)
+    g, iters = run_gpu(a, Y0, n_iter, perms)
+    assert iters == n_iter
+    compare(g, o32, o64, case)
+
+
+def test_parity_stepwise():
+    """After init, after one clustering, after one correction: every exposed field against the oracle."""
+    from harmony_b200.harmony import harmony
+    from oracle.oracle import OracleHarmony
+    from helpers import setup_args
+    (Z, meta) = load_cell_lines(False)
+    a = prepare_inputs(Z, meta, ["cell_type", "dataset"], nclust=30)
+    N, T = Z.shape[0], a["max_iter_kmeans"]
+    Y0 = make_Y0(Z, a["K"], 3)
+    perms = make_perms(N, T, 1)
+    o = OracleHarmony()
+    o.setup(**setup_args(a))
+    g = harmony()
+    g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], T, a["epsilon_kmeans"],
+            a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"], a["batch_proportion_cutoff"])
+    assert (g.N, g.K, g.d, g.B) == (N, 30, 20, 5)
+    np.testing.assert_allclose(g.getZorig().T, Z.astype(np.float32), rtol=0, atol=0)
+    np.testing.assert_allclose(g.getZcorr().T, o.get("Z_corr"), atol=1e-6)
+    np.testing.assert_allclose(g.Pr_b, o.get("Pr_b"), rtol=1e-6)
+    o.init_cluster_cpp(Y0)
+    g.init_cluster_cpp(Y0)
+    np.testing.assert_allclose(g.R.T, o.get("R"), atol=2e-6)
+    np.testing.assert_allclose(g.O.T, o.get("O"), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(g.E.T, o.get("E"), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(g.objective_kmeans, o.trace("objective_kmeans"), rtol=1e-4)
+    o.cluster_cpp(perms)
+    g.cluster_cpp(perms)
+    np.testing.assert_allclose(g.R.T, o.get("R"), atol=1e-5)
+    np.testing.assert_allclose(g.O.T, o.get("O"), rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(g.E.T, o.get("E"), rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(g.objective_kmeans, o.trace("objective_kmeans"), rtol=2e-4)
+    o.moe_correct_ridge_cpp()
+    g.moe_correct_ridge_cpp()
+    assert rel_l2(g.getZcorr().T, o.get("Z_corr")) < 2e-5
+    np.testing.assert_allclose(g.Y.T, o.get("Y"), atol=2e-5)
+    np.testing.assert_allclose(g.getLambda().T, o.get("lambda"), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(g.W.T, o.get("W"), rtol=1e-3, atol=1e-5)
+    g.compute_objective()   # standalone objective == the fused one of the last round
+    ok = g.objective_kmeans
+    np.testing.assert_allclose(ok[-1], ok[-2], rtol=1e-5)
+
+
+def test_small_n_guards_and_errors():
+    # harmony.cpp:83-91 and the error conventions of the C ABI
+    from harmony_b200.harmony import HarmonyError, harmony
+    Z, meta = synthetic(5, 4, [2], seed=1)
+    a = prepare_inputs(Z, meta, "cov0", nclust=2)
+    g = harmony()
+    with pytest.raises(HarmonyError, match="less than 6 cells"):
+        g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], None, 0.2, 4, 1e-3, 1e-2, 2, 0.05, a["B_vec"], 1e-5)
+    Z, meta = synthetic(30, 4, [2], seed=1)
+    a = prepare_inputs(Z, meta, "cov0", nclust=2)
+    g = harmony()
+    with pytest.warns(UserWarning, match="Too few cells"):
+        g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], None, 0.2, 4, 1e-3, 1e-2, 2, 0.05, a["B_vec"], 1e-5)
+    Y0, perms = make_Y0(Z, 2, 0), make_perms(30, 4, 0)
+    g.init_cluster_cpp(Y0)
+    g.cluster_cpp(perms)
+    g.moe_correct_ridge_cpp()
+    o, _, _ = run_oracle(dict(a, epsilon_harmony=-np.inf), Y0, 1, perms=perms.reshape(1, 4, 30))
+    assert rel_l2(g.getZcorr().T, o.get("Z_corr")) < 1e-4
+    g2 = harmony()
+    with pytest.raises(HarmonyError):
+        g2.init_cluster_cpp(Y0)          # before setup
+    bad = perms.copy()
+    bad[0, 0] = 10 ** 6
+    with pytest.raises(HarmonyError, match="outside"):
+        g.cluster_cpp(bad)
+
+
+def test_field_writes_and_resume():
+    """Fields are read-write like the Rcpp module's (.field); the object survives across harmonize calls
+    (vignettes/detailedWalkthrough.Rmd:364, 891-893)."""
+    from harmony_b200.harmony import harmony
+    Z, meta = load_cell_lines(True)
+    a = prepare_inputs(Z, meta, "dataset", nclust=5)
+    g = harmony()
+    g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], None, a["alpha"], 4, 1e-3, 1e-2, 5, 0.05, a["B_vec"], 1e-5)
+    g.init_cluster_cpp(make_Y0(Z, 5, 0))
+    g.max_iter_kmeans = 10
+    assert g.max_iter_kmeans == 10
+    g.cluster_cpp(make_perms(300, 10, 0))
+    assert 5 <= int(g.kmeans_rounds[-1]) <= 10
+    Y = g.Y.copy()
+    g.Y = Y * 1.0
+    np.testing.assert_array_equal(g.Y, Y.astype(np.float32))
+    g.moe_correct_ridge_cpp()
+    g.cluster_cpp(make_perms(300, 10, 1))
+    assert len(g.objective_harmony) == 3

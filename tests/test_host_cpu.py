@@ -1,0 +1,125 @@
+"""CPU tests of the host-side logic and of the C-ABI library's surface (no compute calls: this box
+has no GPU).  Mirrors the argument checks of /root/reference/tests/testthat/test_integration.R:43-55."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from harmony_b200 import _lib, harmony_options, prepare_inputs
+from harmony_b200.harmony_option import check_legacy_args
+from helpers import load_cell_lines
+
+
+def test_library_exports_every_declared_symbol():
+    _lib.build()
+    L = ctypes.CDLL(_lib.SO_PATH)
+    names = _lib.exported_symbols()
+    assert len(names) >= 25
+    for s in names:
+        assert hasattr(L, s), s
+    assert L.hb_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a CUDA device the product path fails loudly (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from harmony_b200.harmony import HarmonyError, harmony
+    with pytest.raises(HarmonyError, match="no usable CUDA device"):
+        harmony()
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(_lib._HERE)
+    for dp, _, files in os.walk(os.path.join(root, "harmony_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the CPU oracle", "").lower() or f == "__init__.py", (dp, f)
+
+
+def test_prepare_inputs_defaults():
+    Z, meta = load_cell_lines(True)
+    a = prepare_inputs(Z, meta, "dataset")
+    assert a["K"] == 10                       # min(round(300/30), 100), R/ui.R:192-194
+    assert a["B_vec"].tolist() == [3]
+    assert a["theta"].tolist() == [2, 2, 2]
+    assert a["lambda_"] is None               # lambda = NULL -> estimation
+    assert a["sigma"].shape == (10,) and np.all(a["sigma"] == 0.1)
+    assert a["max_iter_kmeans"] == 4 and a["block_size"] == 0.05
+    assert a["phi_i"].shape == (300, 1) and a["phi_i"].max() == 2
+    a = prepare_inputs(Z.T, meta, "dataset")  # transposed input is detected (R/ui.R:178-183)
+    assert a["Z"].shape == (300, 20)
+    a2 = prepare_inputs(Z, meta, ["cell_type", "dataset"], theta=[1, 3], lambda_=[0.5, 2.0])
+    assert a2["B_vec"].tolist() == [2, 3]
+    assert a2["theta"].tolist() == [1, 1, 3, 3, 3]
+    assert a2["lambda_"].tolist() == [0, 0.5, 0.5, 2, 2, 2]
+    assert a2["phi_i"][:, 1].min() == 2        # second covariate's levels are offset by B_vec[0]
+    a3 = prepare_inputs(Z, meta, "dataset", lambda_=1.5)
+    assert a3["lambda_"].tolist() == [0, 1.5, 1.5, 1.5]
+    a4 = prepare_inputs(Z, meta, "dataset", early_stop=False)
+    assert a4["epsilon_harmony"] == -np.inf
+    a5 = prepare_inputs(Z, np.asarray(meta["dataset"]), None)   # bare vector -> batch_variable
+    assert a5["vars_use"] == ["batch_variable"]
+    a6 = prepare_inputs(Z, meta, "dataset", options=harmony_options(tau=5), nclust=5)
+    nb = 100.0
+    assert np.allclose(a6["theta"], 2 * (1 - np.exp(-(nb / (5 * 5)) ** 2)))
+
+
+def test_error_messages():
+    # test_integration.R:43-55
+    Z, meta = load_cell_lines(True)
+    with pytest.raises(ValueError):
+        prepare_inputs(Z, meta, "fake_variable")
+    with pytest.raises(ValueError, match="mismatch"):
+        prepare_inputs(Z, meta, "dataset", lambda_=[1, 2])
+    short = {k: v[:-1] for k, v in meta.items()}
+    with pytest.raises(ValueError, match="do not correspond"):
+        prepare_inputs(Z, short, "dataset")
+    with pytest.raises(ValueError, match="positive"):
+        prepare_inputs(Z, meta, "dataset", lambda_=-1.0)
+    with pytest.raises(ValueError, match="theta"):
+        prepare_inputs(Z, meta, "dataset", theta=[1, 2])
+    with pytest.raises(TypeError):
+        prepare_inputs(Z, meta, "dataset", options={"alpha": 1})
+    with pytest.raises(ValueError, match="block.size"):
+        harmony_options(block_size=0)
+    with pytest.raises(TypeError, match="dropped"):
+        check_legacy_args(tau=1)
+    with pytest.raises(TypeError, match="unhandled"):
+        check_legacy_args(foo=1)
+
+
+def test_harmonize_driver_contract():
+    """R/utils.R:15-46 against a scripted stand-in object."""
+    from harmony_b200 import harmonize
+
+    class Fake:
+        def __init__(self, conv_at, status=0):
+            self.calls, self.conv_at, self.status, self.it = [], conv_at, status, 0
+
+        def cluster_cpp(self):
+            self.calls.append("cluster")
+            return self.status
+
+        def moe_correct_ridge_cpp(self):
+            self.calls.append("moe")
+
+        def check_convergence(self, t):
+            assert t == 1
+            self.it += 1
+            return self.it >= self.conv_at
+
+    f = Fake(3)
+    assert harmonize(f, 10, verbose=False) == 0
+    assert f.calls == ["cluster", "moe"] * 3
+    f = Fake(99)
+    assert harmonize(f, 2, verbose=False) is None
+    assert len(f.calls) == 4
+    assert harmonize(Fake(1), 0, verbose=False) == 0
+    with pytest.raises(KeyboardInterrupt):
+        harmonize(Fake(1, status=-1), 3, verbose=False)
+    with pytest.raises(RuntimeError, match="non-zero exit status: 7"):
+        harmonize(Fake(1, status=7), 3, verbose=False)
