@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — cells / second / Harmony-iteration on synthetic embeddings (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One *step* = one trip of the harmonize() loop body (R/utils.R:20-45): cluster_cpp (cold-start
+re-estimate + T=4 x (update_R + compute_objective)) + moe_correct_ridge_cpp + check_convergence(1),
+defaults of R/harmony_option.R:33-40, early_stop = FALSE.  Workload at N=1: BASELINE.json config 3
+(synthetic 1M cells x 50 PCs, 1 covariate with 20 batches, K=100).  Weak scaling: every rank holds
+CELLS_PER_GPU cells of one global problem (cells sharded, global statistics all-reduced).
+
+The JSON line carries `value` (device-resident, CUDA-event timed on the library's stream, max over
+ranks), `e2e` (the same metric through the public API with HOST buffers: setup H2D + init + iterations +
+getZcorr D2H), `roofline` (dominant kernel, algorithmic bytes / measured launch time, against
+MEASURED_PEAKS.json) and `cpu_baseline` (the CPU oracle = restatement of the reference, timed on this
+box's host cores on a bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CELLS_PER_GPU = 1_000_000
+D, K, B_LEVELS, T = 50, 100, 20, 4
+N_TYPES = 30
+METRIC = "cells/sec/Harmony-iteration (50 PCs, K=100)"
+# algorithmic bytes per cell per Harmony iteration, fp32 state, T = 4
+ALGO_BYTES_PER_CELL_ITER = 4 * (K * (3 + 2 * T) + D * (5 + T)) + 4 * (T + 2)   # 6224 for K=100, d=50
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def synth_shard(n, cell_offset, seed, d=D, n_levels=B_LEVELS, n_types=N_TYPES):
+    """SURVEY.md §8(d) generator: Z[i,j] = sd_j (M[t_i,j] + 0.5 S[b_i,j] + 0.6 eps), sd_j = 10/sqrt(1+j);
+    type probabilities ~ Dirichlet(2), batch probabilities ~ LogNormal(0, 0.5).  Global parameters come
+    from `seed`, the per-cell draws from (seed, cell_offset) so shards are consistent for any world size."""
+    g = np.random.default_rng(seed)
+    M = g.standard_normal((n_types, d)).astype(np.float32)
+    S = g.standard_normal((n_levels, d)).astype(np.float32)
+    p_type = g.dirichlet(np.full(n_types, 2.0))
+    p_lvl = g.lognormal(0.0, 0.5, n_levels)
+    p_lvl /= p_lvl.sum()
+    sd = (10.0 / np.sqrt(1.0 + np.arange(d))).astype(np.float32)
+    r = np.random.default_rng([seed, cell_offset])
+    t = r.choice(n_types, n, p=p_type)
+    b = r.choice(n_levels, n, p=p_lvl).astype(np.int32)
+    Z = M[t] + 0.5 * S[b] + 0.6 * r.standard_normal((n, d), dtype=np.float32)
+    Z *= sd[None, :]
+    return Z.astype(np.float64), b
+
+
+def host_Y0(Z, k, seed):
+    """Initial centroids (stand-in for kmeans_centers, outside the timed path): k distinct random cells of
+    a subsample + 2 Lloyd iterations on the cosine-normalised subsample."""
+    rng = np.random.default_rng(seed)
+    sub = Z[rng.choice(Z.shape[0], min(Z.shape[0], 50_000), replace=False)]
+    sub = sub / np.maximum(np.linalg.norm(sub, axis=1, keepdims=True), 1e-30)
+    Y = sub[rng.choice(sub.shape[0], k, replace=False)].copy()
+    for _ in range(2):
+        a = np.argmax(sub @ Y.T, axis=1)
+        for j in range(k):
+            if np.any(a == j):
+                Y[j] = sub[a == j].mean(axis=0)
+    return Y
+
+
+def setup_kwargs(b, n_levels=B_LEVELS):
+    theta = np.full(n_levels, 2.0)
+    return dict(phi=b.reshape(-1, 1), sigma=np.full(K, 0.1), theta=theta, lambda_=None, alpha=0.2,
+                max_iter_kmeans=T, epsilon_kmeans=1e-3, epsilon_harmony=-np.inf, K=K, block_size=0.05,
+                B_vec=np.array([n_levels], dtype=np.int32), cutoff=1e-5)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def cpu_reference_run(n_cells, iters, threads, seed=20260925):
+    """Times the CPU oracle (restatement of the reference's Armadillo/OpenBLAS path) on host cores."""
+    from oracle.oracle import OracleHarmony, load_blas
+    blas = load_blas(threads)
+    Z, b = synth_shard(n_cells, 0, seed)
+    kw = setup_kwargs(b)
+    Y0 = host_Y0(Z, K, 1)
+    o = OracleHarmony()
+    o.setup(Z, kw["phi"], kw["B_vec"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, 1e-5)
+    o.init_cluster_cpp(Y0)
+    rng = np.random.default_rng(5)
+    times = []
+    for it in range(iters + 1):             # iteration 1 skips the cold start -> untimed
+        perms = np.stack([rng.permutation(n_cells) for _ in range(T)]).astype(np.int64)
+        t0 = time.perf_counter()
+        o.cluster_cpp(perms)
+        o.moe_correct_ridge_cpp()
+        o.check_convergence(1)
+        if it > 0:
+            times.append(time.perf_counter() - t0)
+    return float(np.median(times)), blas
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port) with all host BLAS threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = 200_000
+    steps = max(1, min(args.steps, 3))
+    t_iter, blas = cpu_reference_run(n_sample, steps, cores)
+    v = n_sample / t_iter
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s/iter", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": t_iter * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic {n_sample} cells x {D} PCs, 1 covariate ({B_LEVELS} batches), K={K}"
+                                   " (bounded sample of config 3; the algorithm is O(N))"},
+            "cpu_baseline": {"value": v, "unit": "cells/s/iter", "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} cells, {steps} timed iteration(s), BLAS={os.path.basename(blas)}"},
+            "e2e": {"value": v, "unit": "cells/s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells-per-gpu", type=int, default=CELLS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from harmony_b200.harmony import harmony
+    from harmony_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    n_local = args.cells_per_gpu
+    N_global = n_local * world
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import ctypes
+        uid = ctypes.create_string_buffer(128)
+        if rank == 0:
+            assert _lib.lib().hb_comm_unique_id(uid) == 0
+        t = torch.tensor(list(uid.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        comm = (rank, world, bytes(t.cpu().tolist()), N_global, rank * n_local)
+
+    seed = 20260922 + 3
+    Z, b = synth_shard(n_local, rank * n_local, seed)
+    kw = setup_kwargs(b)
+    Y0 = host_Y0(Z, K, 1) if rank == 0 else np.zeros((K, D))
+    if world > 1:
+        ty = torch.from_numpy(Y0).cuda()
+        dist.broadcast(ty, 0)
+        Y0 = ty.cpu().numpy()
+
+    def make_obj():
+        g = harmony(device=local_rank, comm=comm)
+        g.setup(Z, kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, kw["B_vec"],
+                kw["cutoff"])
+        g.set_seed(1234)
+        g.init_cluster_cpp(Y0)
+        return g
+
+    def step(g):
+        st = g.cluster_cpp()
+        assert st == 0
+        g.moe_correct_ridge_cpp()
+        g.check_convergence(1)
+
+    g = make_obj()
+    stream = torch.cuda.ExternalStream(g.cuda_stream, device=torch.device("cuda", local_rank))
+    for _ in range(max(3, args.warmup)):
+        step(g)
+    g.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = g.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(g)
+    e1.record(stream)
+    g.synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = g.kernel_launches - l0
+    if world > 1:
+        dist.barrier()
+        tm = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    value = N_global / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing pass (region timers: CUDA events on the library stream, extra syncs) -> roofline
+    peaks, peak_kind = measured_peaks()
+    g.enable_timing(True)
+    base = {r: g.region_time(r) for r in ("k_block_update", "k_block_colsum", "k_step_prepare", "assign", "plan",
+                                           "ridge_stats", "ridge_solve", "ridge_apply", "update_R")}
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step(g)
+    g.synchronize()
+    reg = {}
+    for r, (ms0, n0) in base.items():
+        ms1, n1 = g.region_time(r)
+        reg[r] = {"ms_per_step": (ms1 - ms0) / prof_steps, "launches_per_step": (n1 - n0) / prof_steps}
+    g.enable_timing(False)
+    nb = 20
+    upd = reg["k_block_update"]
+    roofline = None
+    if upd["launches_per_step"] > 0 and upd["ms_per_step"] > 0:
+        # k_block_update: per cell of the block it reads U (4K B) + its order entry (4 B) and writes R (4K B)
+        cells_per_launch = n_local / nb
+        algo_bytes = cells_per_launch * (8 * K + 4)
+        t_launch = upd["ms_per_step"] / upd["launches_per_step"] * 1e-3
+        ach = algo_bytes / t_launch / 1e9
+        roofline = {"kernel": "k_block_update", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                    "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_us": t_launch * 1e6,
+                    "share_of_step": upd["ms_per_step"] / max(1e-9, sum(
+                        reg[r]["ms_per_step"] for r in ("update_R", "assign", "plan", "ridge_stats", "ridge_solve",
+                                                        "ridge_apply")))}
+    step_ach = ALGO_BYTES_PER_CELL_ITER * n_local / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: public API with host buffers (pinned), H2D of inputs and D2H of the result in the timed region
+    e2e = None
+    if not args.no_e2e:
+        del g
+        iters_e2e = 10                                  # RunHarmony's default max_iter (R/ui.R:98)
+        Zp = torch.from_numpy(Z).pin_memory().numpy()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g2 = harmony(device=local_rank, comm=comm)
+        g2.setup(Zp, kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, kw["B_vec"],
+                 kw["cutoff"])
+        g2.set_seed(1234)
+        g2.init_cluster_cpp(Y0)
+        for _ in range(iters_e2e):
+            step(g2)
+        out = g2.getZcorr()
+        g2.synchronize()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t_e2e], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt.item())
+        assert np.all(np.isfinite(out[:, :8]))
+        e2e = {"value": N_global * iters_e2e / t_e2e, "unit": "cells/s/iter",
+               "h2d_bytes_per_step": int((Z.nbytes + kw["phi"].nbytes) * world / iters_e2e),
+               "d2h_bytes_per_step": int(out.nbytes * world / iters_e2e),
+               "iterations": iters_e2e, "seconds": t_e2e,
+               "what": "harmony() + setup (H2D, pinned host Z fp64) + init_cluster_cpp + 10 x harmonize body + "
+                       "getZcorr (D2H fp64); bytes are per iteration (totals / 10)"}
+        del g2
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sample = 200_000
+        t_iter, blas = cpu_reference_run(n_sample, 2, 1)
+        cpu = {"value": n_sample / t_iter, "unit": "cells/s/iter", "cores": 1, "kind": "port",
+               "sample": f"{n_sample} cells x {D} PCs, K={K}, {B_LEVELS} batches, 2 timed iterations, single thread "
+                         f"(reference default ncores=1), sgemm from {os.path.basename(blas)}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "cells/s/iter", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"synthetic {N_global} cells x {D} PCs, 1 covariate ({B_LEVELS} batches), "
+                                       f"K={K}, T={T}, block_size=0.05 (BASELINE.json config 3 per GPU)",
+                           "cells_per_gpu": n_local, "parallelism": f"cells sharded x{world}",
+                           "l2": "state (U,R,Z = 1.2 GB per GPU) is ~10x larger than the 126 MB L2"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline,
+                "roofline_step": {"bound": "hbm", "achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": step_ach / peaks["hbm_gbs"],
+                                  "algorithmic_bytes_per_cell_iter": ALGO_BYTES_PER_CELL_ITER},
+                "regions_ms_per_step": {r: round(v["ms_per_step"], 4) for r, v in reg.items()},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -185,18 +185,25 @@ struct RegionScope {
   hb_handle* h;
   const char* name;
   int64_t l0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   RegionScope(hb_handle* h_, const char* n) : h(h_), name(n), l0(h_->launches) {
-    if (h->timing) cudaEventRecord(h->ev0, h->stream);
+    if (h->timing) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, h->stream);
+    }
   }
   ~RegionScope() {
     Region& r = h->regions[name];
     r.launches += h->launches - l0;
-    if (h->timing) {
-      cudaEventRecord(h->ev1, h->stream);
-      cudaEventSynchronize(h->ev1);
+    if (e0) {
+      cudaEventRecord(e1, h->stream);
+      cudaEventSynchronize(e1);
       float ms = 0;
-      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      cudaEventElapsedTime(&ms, e0, e1);
       r.ms += ms;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
     }
   }
 };
@@ -426,18 +433,23 @@ int run_update_R(hb_handle* h) {
         a.blk = j;
         a.acc_O = rem_O;
         a.acc_rs = rem_rs;
+        RegionScope r1(h, "k_block_colsum");
         k_block_colsum<KQ><<<grid, ROW_THREADS, sm_col, h->stream>>>(a);
         CKL();
       }
       TRY(allreduce_f(h, sl, slot));
-      k_step_prepare<<<(B * K + 255) / 256, 256, 0, h->stream>>>(h->O.p, h->E.p, add_O, add_rs, rem_O, rem_rs,
-                                                                  h->Pr_b.p, h->theta.p, (j < nb) ? h->P.p : nullptr, B, K);
-      CKL();
+      {
+        RegionScope r2(h, "k_step_prepare");
+        k_step_prepare<<<(B * K + 255) / 256, 256, 0, h->stream>>>(h->O.p, h->E.p, add_O, add_rs, rem_O, rem_rs,
+                                                                    h->Pr_b.p, h->theta.p, (j < nb) ? h->P.p : nullptr, B, K);
+        CKL();
+      }
       CK(cudaMemsetAsync(sl, 0, sizeof(float) * slot, h->stream));
       if (j < nb) {
         float* nx = h->acc.p + (size_t)((j + 1) & 1) * slot;  // add_j goes to slot j+1
         a.acc_O = nx;
         a.acc_rs = nx + (size_t)B * K;
+        RegionScope r3(h, "k_block_update");
         k_block_update<KQ><<<grid, ROW_THREADS, sm_upd, h->stream>>>(a);
         CKL();
       }

@@ -128,6 +128,8 @@ class harmony:
             self._check(self._L.hb_init_cluster(self._h, None))
             return
         K, d = self._scalar("K"), self._scalar("d")
+        if K == 0:                                    # setup has not run: let the library report it
+            self._check(self._L.hb_init_cluster(self._h, None))
         Y0 = np.asarray(Y0, dtype=np.float64)
         if Y0.shape == (d, K) and not (K == d and Y0.flags.c_contiguous):
             Y0 = Y0.T

@@ -47,19 +47,21 @@ def argmax_mismatch_outside_band(Rg, Ro):
 
 def compare(g, o32, o64, label):
     Zg, Z32, Z64 = g.getZcorr().T, o32.get("Z_corr"), o64.get("Z_corr")
-    Rg, R32 = g.R.T, o32.get("R")
+    Rg, R32, R64 = g.R.T, o32.get("R"), o64.get("R")
     e_g32, e_g64, e_3264 = rel_l2(Zg, Z32), rel_l2(Zg, Z64), rel_l2(Z32, Z64)
     bad, anydiff = argmax_mismatch_outside_band(Rg, R32)
     dR = float(np.abs(Rg - R32).max())
+    dR64, dR3264 = float(np.abs(Rg - R64).max()), float(np.abs(R32 - R64).max())
     dY = float(np.abs(g.Y.T - o32.get("Y")).max())
     dO = float(np.abs(g.O.T - o32.get("O")).max() / max(1.0, np.abs(o32.get("O")).max()))
     print(f"[{label}] relL2(Z gpu,o32)={e_g32:.2e} (gpu,o64)={e_g64:.2e} (o32,o64)={e_3264:.2e} "
-          f"max|dR|={dR:.2e} max|dY|={dY:.2e} rel|dO|={dO:.2e} argmax diff={anydiff} outside band={bad}")
+          f"max|dR|={dR:.2e} (vs o64 {dR64:.2e}; o32 vs o64 {dR3264:.2e}) max|dY|={dY:.2e} rel|dO|={dO:.2e} argmax diff={anydiff} outside band={bad}")
     assert np.all(np.isfinite(Zg))
     assert e_g32 <= TOL_Z
     assert e_g64 <= 2 * e_3264 + 2e-5
     assert bad == 0
-    assert dR <= 5e-4
+    # the fp32 oracle carries the reference's own sequential-sum noise: judge R against the fp64 truth
+    assert dR64 <= 2 * dR3264 + 1e-5, (dR64, dR3264)
     np.testing.assert_allclose(Rg.sum(axis=1), 1.0, atol=1e-5)
     # traces: same lengths, values within fp32 summation noise of the fp64 truth
     for name in ("objective_kmeans", "objective_harmony", "objective_kmeans_dist", "objective_kmeans_entropy",
