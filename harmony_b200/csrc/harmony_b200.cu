@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "update_kernel.cuh"
 
 namespace {
 
@@ -105,6 +106,7 @@ struct hb_handle {
   int64_t N_global = 0, cell_offset = 0, n = 0;
   bool shard_set = false;
   int d = 0, K = 0, B = 0, C = 0, J = 0;
+  int KS = 0, DS = 0;  // row strides (multiples of 4 floats) of U/R/O/E and of Zo/Zc
   std::vector<int> B_vec, cov_of;
   float block_size = 0, epsilon_kmeans = 0, epsilon_harmony = 0, alpha = 0, cutoff = 0;
   unsigned max_iter_kmeans = 0, window_size = 3;
@@ -119,6 +121,12 @@ struct hb_handle {
 
   // device state
   DevBuf<float> Zo, Zc, U, R, Y, sigma, theta, Pr_b, N_b, lambda, O, E, P, Oacc, acc, S, V, Wfull, scratch, trace_d;
+  DevBuf<float> ring, acc2, Psave, OEend, tmpT;  // persistent update kernel state
+  DevBuf<double> obj2;
+  DevBuf<unsigned> bar;
+  int plan_rounds = 0;   // rounds the plan buffers hold
+  bool use_v2 = true;
+  int coop_grid = 0;
   DevBuf<double> obj_acc, stage;
   DevBuf<int> sort_perm, inv_sort, tuple_levels, cov_of_d, tile_cell0, tile_len, tile_tuple, chunk_start,
       tuple_chunk0, blk_of, order, H, seg_start, tile_base, iscratch, skipped, err_flag;
@@ -249,9 +257,9 @@ int dispatch_kq(hb_handle* h, int K, F&& f) {
 // ---- K1 launcher: assignment from centroids (init + cold start) -------------------------------
 int run_assign(hb_handle* h, bool normalise) {
   RegionScope rs(h, "assign");
-  const int K = h->K, d = h->d, B = h->B;
+  const int K = h->K, d = h->d, B = h->B, KS = h->KS;
   const int KP = (K + 63) & ~63, DP4 = (d + 3) & ~3;
-  CK(cudaMemsetAsync(h->Oacc.p, 0, sizeof(float) * ((size_t)B * K + K), h->stream));
+  CK(cudaMemsetAsync(h->Oacc.p, 0, sizeof(float) * ((size_t)B * KS + KS), h->stream));
   AssignArgs a;
   a.Zc = h->Zc.p;
   a.Y = h->Y.p;
@@ -263,13 +271,15 @@ int run_assign(hb_handle* h, bool normalise) {
   a.tile_tuple = h->tile_tuple.p;
   a.tuple_levels = h->tuple_levels.p;
   a.O_acc = h->Oacc.p;
-  a.rs_acc = h->Oacc.p + (size_t)B * K;
+  a.rs_acc = h->Oacc.p + (size_t)B * KS;
   a.obj_acc = h->obj_acc.p;
   a.ntiles = h->ntiles;
   a.d = d;
   a.K = K;
   a.C = h->C;
   a.KP = KP;
+  a.DS = h->DS;
+  a.KS = KS;
   a.normalise = normalise ? 1 : 0;
   size_t smem = sizeof(float) * ((size_t)DP4 * KP + (size_t)TM * DP4 + (size_t)TM * (KP + 4) + KP + (size_t)NWARP * KP);
   if (smem > 227 * 1024) return fail(h, 2, "K*d too large for the assignment kernel (needs %zu B shared memory)", smem);
@@ -286,9 +296,9 @@ int run_assign(hb_handle* h, bool normalise) {
     return 0;
   });
   TRY(st);
-  TRY(allreduce_f(h, h->Oacc.p, (size_t)B * K + K));
-  k_assign_finalize<<<(B * K + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * K, h->Pr_b.p,
-                                                                 h->O.p, h->E.p, B, K);
+  TRY(allreduce_f(h, h->Oacc.p, (size_t)B * KS + KS));
+  k_assign_finalize<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * KS, h->Pr_b.p,
+                                                                  h->O.p, h->E.p, B, K, KS);
   CKL();
   return 0;
 }
@@ -309,16 +319,17 @@ int ensure_trace_cap(hb_handle* h, int slots) {
   return 0;
 }
 
-// obj_acc holds this rank's per-cell sums; fold in the K x B cross term and append to the device trace
-int push_objective(hb_handle* h) {
+// obj holds this rank's per-cell sums; fold in the K x B cross term of tables (O, E) and append to the trace
+int push_objective_from(hb_handle* h, const float* O, const float* E, double* obj) {
   TRY(ensure_trace_cap(h, h->obj_count + 1));
-  TRY(allreduce_d(h, h->obj_acc.p, 2));
-  k_objective_finalize<<<1, 256, 0, h->stream>>>(h->O.p, h->E.p, h->theta.p, h->sigma.p, h->obj_acc.p, h->trace_d.p,
-                                                  h->obj_count, h->B, h->K, (double)h->N_global, 1.0);
+  TRY(allreduce_d(h, obj, 2));
+  k_objective_finalize<<<1, 256, 0, h->stream>>>(O, E, h->theta.p, h->sigma.p, obj, h->trace_d.p, h->obj_count, h->B,
+                                                  h->K, h->KS, (double)h->N_global, 1.0);
   CKL();
   h->obj_count++;
   return 0;
 }
+int push_objective(hb_handle* h) { return push_objective_from(h, h->O.p, h->E.p, h->obj_acc.p); }
 
 int sync_traces(hb_handle* h) {
   if (h->obj_synced == h->obj_count) return 0;
@@ -359,56 +370,62 @@ int check_convergence_host(hb_handle* h, int type, int* out) {
   return 0;
 }
 
-// ---- update-order plan ---------------------------------------------------------------------------
-int build_plan(hb_handle* h, const int64_t* perm_d /* device, N_global, or null */) {
+// ---- update-order plan of round t (buffers hold plan_rounds rounds) ------------------------------
+int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, or null */) {
   RegionScope rs(h, "plan");
   const int nb = h->nb, J = h->J, nc = h->nchunks;
   const int64_t n = h->n;
+  const int S = nb * J;
+  int* blk_of = h->blk_of.p + (size_t)t * n;
+  int* order = h->order.p + (size_t)t * n;
+  int* seg_start = h->seg_start.p + (size_t)t * (S + 1);
+  int* tile_base = h->tile_base.p + (size_t)t * (S + 1);
   if (perm_d) {
-    CK(cudaMemsetAsync(h->blk_of.p, 0xff, sizeof(int) * (size_t)n, h->stream));
+    CK(cudaMemsetAsync(blk_of, 0xff, sizeof(int) * (size_t)n, h->stream));
     k_plan_block_injected<<<grid_for(h->N_global, 256, h->num_sms * 8), 256, 0, h->stream>>>(
-        perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, nb, h->blk_of.p, h->err_flag.p);
+        perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, nb, blk_of, h->err_flag.p);
     CKL();
   } else {
     uint64_t key = hb_mix64(h->seed ^ hb_mix64(h->round_counter + 0x1234567ull));
     k_plan_block_native<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
-        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, nb, h->half_bits, key, h->blk_of.p);
+        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, nb, h->half_bits, key, blk_of);
     CKL();
   }
   h->round_counter++;
   const int wpb = 8;  // warps per block
   size_t sm = sizeof(int) * (size_t)wpb * nb;
-  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(h->blk_of.p, h->chunk_start.p, nc, nb, h->H.p);
+  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(blk_of, h->chunk_start.p, nc, nb, h->H.p);
   CKL();
   k_scan_exclusive<<<1, 1024, 0, h->stream>>>(h->H.p, (int64_t)nb * nc, nullptr);
   CKL();
-  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(h->blk_of.p, h->chunk_start.p, nc, nb, h->H.p,
-                                                                     h->order.p);
+  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(blk_of, h->chunk_start.p, nc, nb, h->H.p, order);
   CKL();
-  const int S = nb * J;
   k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
-                                                                    h->seg_start.p, h->tile_base.p);
+                                                                    seg_start, tile_base);
   CKL();
-  k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->seg_start.p, S, h->tile_base.p);
-  CKL();
-  k_scan_exclusive<<<1, 1024, 0, h->stream>>>(h->tile_base.p, (int64_t)S + 1, nullptr);
-  CKL();
+  if (!h->use_v2) {
+    k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(seg_start, S, tile_base);
+    CKL();
+    k_scan_exclusive<<<1, 1024, 0, h->stream>>>(tile_base, (int64_t)S + 1, nullptr);
+    CKL();
+  }
   return 0;
 }
 
-// ---- one update_R sweep (harmony.cpp:269-342) --------------------------------------------------
-int run_update_R(hb_handle* h) {
+// ---- v1: one update_R sweep (harmony.cpp:269-342), three launches per block step ------------------
+int run_update_R_v1(hb_handle* h, int t) {
   RegionScope rs(h, "update_R");
-  const int K = h->K, B = h->B, nb = h->nb;
+  const int K = h->K, B = h->B, nb = h->nb, KS = h->KS;
   const int KP = (K + 63) & ~63;
-  const size_t slot = 2 * ((size_t)B * K + K);  // [add_O | add_rs | rem_O | rem_rs]
+  const size_t slot = 2 * ((size_t)B * KS + KS);  // [add_O | add_rs | rem_O | rem_rs]
+  const int S = nb * h->J;
   CK(cudaMemsetAsync(h->acc.p, 0, sizeof(float) * 2 * slot, h->stream));
   StepArgs a;
   a.U = h->U.p;
   a.R = h->R.p;
-  a.order = h->order.p;
-  a.seg_start = h->seg_start.p;
-  a.tile_base = h->tile_base.p;
+  a.order = h->order.p + (size_t)t * h->n;
+  a.seg_start = h->seg_start.p + (size_t)t * (S + 1);
+  a.tile_base = h->tile_base.p + (size_t)t * (S + 1);
   a.tuple_levels = h->tuple_levels.p;
   a.sigma = h->sigma.p;
   a.P = h->P.p;
@@ -417,6 +434,7 @@ int run_update_R(hb_handle* h) {
   a.K = K;
   a.C = h->C;
   a.KP = KP;
+  a.KS = KS;
   const int tiles_bound = (int)std::min<int64_t>((h->n / std::max(1, nb)) / TM + h->J + 8, (int64_t)h->num_sms * 8);
   const int grid = std::max(1, tiles_bound);
   const size_t sm_col = sizeof(float) * (size_t)NWARP * KP;
@@ -426,9 +444,9 @@ int run_update_R(hb_handle* h) {
     for (int j = 0; j <= nb; ++j) {
       float* sl = h->acc.p + (size_t)(j & 1) * slot;  // slot j = [add_{j-1} | rem_j]
       float* add_O = sl;
-      float* add_rs = sl + (size_t)B * K;
-      float* rem_O = sl + (size_t)B * K + K;
-      float* rem_rs = rem_O + (size_t)B * K;
+      float* add_rs = sl + (size_t)B * KS;
+      float* rem_O = sl + (size_t)B * KS + KS;
+      float* rem_rs = rem_O + (size_t)B * KS;
       if (j < nb) {
         a.blk = j;
         a.acc_O = rem_O;
@@ -440,15 +458,15 @@ int run_update_R(hb_handle* h) {
       TRY(allreduce_f(h, sl, slot));
       {
         RegionScope r2(h, "k_step_prepare");
-        k_step_prepare<<<(B * K + 255) / 256, 256, 0, h->stream>>>(h->O.p, h->E.p, add_O, add_rs, rem_O, rem_rs,
-                                                                    h->Pr_b.p, h->theta.p, (j < nb) ? h->P.p : nullptr, B, K);
+        k_step_prepare<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->O.p, h->E.p, add_O, add_rs, rem_O, rem_rs,
+                                                                     h->Pr_b.p, h->theta.p, (j < nb) ? h->P.p : nullptr, B, K, KS);
         CKL();
       }
       CK(cudaMemsetAsync(sl, 0, sizeof(float) * slot, h->stream));
       if (j < nb) {
         float* nx = h->acc.p + (size_t)((j + 1) & 1) * slot;  // add_j goes to slot j+1
         a.acc_O = nx;
-        a.acc_rs = nx + (size_t)B * K;
+        a.acc_rs = nx + (size_t)B * KS;
         RegionScope r3(h, "k_block_update");
         k_block_update<KQ><<<grid, ROW_THREADS, sm_upd, h->stream>>>(a);
         CKL();
@@ -456,6 +474,129 @@ int run_update_R(hb_handle* h) {
     }
     return 0;
   });
+}
+
+// ---- v2: persistent cooperative kernel over rounds [t0, t1) of this cluster_cpp call --------------
+int nv_for(int KS) {
+  int nv = 1;
+  while (32 * nv < KS) nv <<= 1;
+  return nv;
+}
+template <typename F>
+int dispatch_nv(hb_handle* h, int KS, F&& f) {
+  switch (nv_for(KS)) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 8: return f(std::integral_constant<int, 8>());
+  }
+  return fail(h, 2, "K = %d is not supported by the persistent update kernel", h->K);
+}
+size_t upd_smem_bytes(const hb_handle* h) {
+  return sizeof(float) * ((size_t)3 * h->KS + (size_t)UPD_WARPS * h->KS + (size_t)h->nb * h->KS) +
+         sizeof(int) * ((size_t)h->J + 1);
+}
+UpdArgs make_upd_args(hb_handle* h, int T) {
+  UpdArgs a;
+  a.U = h->U.p;
+  a.R = h->R.p;
+  a.order = h->order.p;
+  a.seg_start = h->seg_start.p;
+  a.blk_of = h->blk_of.p;
+  a.tuple_levels = h->tuple_levels.p;
+  a.sigma = h->sigma.p;
+  a.theta = h->theta.p;
+  a.Pr_b = h->Pr_b.p;
+  a.ring = h->ring.p;
+  a.acc = h->acc2.p;
+  a.Psave = h->Psave.p;
+  a.OEend = h->OEend.p;
+  a.obj = h->obj2.p;
+  a.bar = h->bar.p;
+  a.n = h->n;
+  a.K = h->K;
+  a.KS = h->KS;
+  a.C = h->C;
+  a.J = h->J;
+  a.B = h->B;
+  a.nb = h->nb;
+  a.T = T;
+  a.first_round_from_R = 1;
+  return a;
+}
+// zero the per-step accumulators and seed ring[1] (= "O_{-1}") with the current tables
+int upd_begin_call(hb_handle* h, int T) {
+  const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
+  CK(cudaMemsetAsync(h->acc2.p, 0, sizeof(float) * SL * ((size_t)T * h->nb + 2), h->stream));
+  CK(cudaMemsetAsync(h->obj2.p, 0, sizeof(double) * 2 * (size_t)T, h->stream));
+  CK(cudaMemcpyAsync(h->ring.p + 2 * BK, h->O.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->ring.p + 3 * BK, h->E.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+int upd_launch(hb_handle* h, UpdArgs a, bool cooperative) {
+  const size_t smem = upd_smem_bytes(h);
+  return dispatch_nv(h, h->KS, [&](auto nvc) -> int {
+    constexpr int NV = decltype(nvc)::value;
+    CK(cudaFuncSetAttribute(k_update_steps<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (h->coop_grid == 0) {
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_update_steps<NV>, UPD_THREADS, smem));
+      if (occ < 1) return fail(h, 2, "persistent update kernel does not fit on an SM");
+      h->coop_grid = h->num_sms;  // one CTA per SM
+    }
+    a.use_barrier = cooperative ? 1 : 0;
+    if (cooperative) {
+      void* args[] = {&a};
+      CK(cudaLaunchCooperativeKernel((void*)k_update_steps<NV>, dim3(h->coop_grid), dim3(UPD_THREADS), args, smem, h->stream));
+    } else {
+      k_update_steps<NV><<<h->coop_grid, UPD_THREADS, smem, h->stream>>>(a);
+    }
+    CKL();
+    return 0;
+  });
+}
+// rounds [t0, t1): t0 == 0 runs the prologue look-ahead.  write_mask: rounds that store R.
+int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
+  RegionScope rs(h, "update_R");
+  const int nb = h->nb;
+  const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
+  UpdArgs a = make_upd_args(h, T);
+  a.write_R_mask = write_mask;
+  if (h->world <= 1) {
+    a.s_begin = t0 * nb;
+    a.s_end = t1 * nb;
+    a.prologue = (t0 == 0) ? 1 : 0;
+    RegionScope r3(h, "k_update_steps");
+    TRY(upd_launch(h, a, true));
+  } else {
+    // NCCL mode: one launch per step, the step's slot [add_{s-1} | rem_s] all-reduced in between
+    if (t0 == 0) {
+      a.s_begin = a.s_end = 0;
+      a.prologue = 1;
+      TRY(upd_launch(h, a, false));
+    }
+    a.prologue = 0;
+    for (int s = t0 * nb; s < t1 * nb; ++s) {
+      TRY(allreduce_f(h, h->acc2.p + (size_t)(s + 1) * SL, SL));
+      a.s_begin = s;
+      a.s_end = s + 1;
+      TRY(upd_launch(h, a, false));
+    }
+    TRY(allreduce_f(h, h->acc2.p + (size_t)(t1 * nb + 1) * SL, SL));  // slot(S): add_{S-1} (+ look-ahead rem_S)
+  }
+  // tables at the end of round t1-1 -> O, E (the chain itself continues from the ring)
+  {
+    RegionScope r4(h, "k_update_finalize");
+    k_update_finalize<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
+    CKL();
+  }
+  // compute_objective() of every round in [t0, t1) (harmony.cpp:248)
+  for (int t = t0; t < t1; ++t) {
+    const float* O = (t == t1 - 1) ? h->O.p : h->OEend.p + (size_t)t * 2 * BK;
+    const float* E = (t == t1 - 1) ? h->E.p : h->OEend.p + (size_t)t * 2 * BK + BK;
+    TRY(push_objective_from(h, O, E, h->obj2.p + 2 * (size_t)t));
+  }
+  return 0;
 }
 
 // ---- moe_correct_ridge_cpp (harmony.cpp:345-638) -------------------------------------------------
@@ -476,6 +617,8 @@ int run_correct(hb_handle* h) {
     a.d = d;
     a.K = K;
     a.KS = (K <= 128) ? K : 128;
+    a.ldR = h->KS;
+    a.ldZ = h->DS;
     const int KSP = (a.KS + 7) & ~7, DP = (D1 + 3) & ~3;
     dim3 block(DP / 4, KSP / 8);
     if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the statistics kernel", d);
@@ -509,6 +652,7 @@ int run_correct(hb_handle* h) {
     a.B = B;
     a.C = C;
     a.d = d;
+    a.KS = h->KS;
     a.alpha = h->alpha;
     a.cutoff = h->cutoff;
     k_ridge_solve<<<K, 256, sizeof(int) * (size_t)(B + C), h->stream>>>(a);
@@ -527,6 +671,8 @@ int run_correct(hb_handle* h) {
     a.ntiles = h->ntiles;
     a.d = d;
     a.K = K;
+    a.ldR = h->KS;
+    a.ldZ = h->DS;
     const int DP = (d + 3) & ~3, KP4 = (K + 3) & ~3;
     dim3 block(DP / 4, TM / 4);
     if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the apply kernel", d);
@@ -555,14 +701,14 @@ int check_err_flag(hb_handle* h) {
   return 0;
 }
 
-// rows of a per-cell field, un-sorted and widened to double, through a bounded staging buffer
-int download_rows(hb_handle* h, const float* src, int cols, double* out) {
+// rows of a per-cell field (device row stride ld), un-sorted and widened to double, via a bounded staging buffer
+int download_rows(hb_handle* h, const float* src, int cols, int ld, double* out) {
   const int64_t n = h->n;
   const int64_t rows_per = std::max<int64_t>(1, (int64_t)(h->stage.n / (size_t)cols));
   for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
     int64_t rows = std::min(rows_per, n - r0);
     k_download_rows<<<grid_for(rows * cols, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, h->stage.p, h->inv_sort.p,
-                                                                                        r0, rows, cols);
+                                                                                        r0, rows, cols, ld);
     CKL();
     CK(cudaMemcpyAsync(out + r0 * cols, h->stage.p, sizeof(double) * (size_t)rows * cols, cudaMemcpyDeviceToHost,
                        h->stream));
@@ -570,7 +716,7 @@ int download_rows(hb_handle* h, const float* src, int cols, double* out) {
   }
   return 0;
 }
-int upload_rows(hb_handle* h, const double* in, int cols, float* dst) {
+int upload_rows(hb_handle* h, const double* in, int cols, int ld, float* dst) {
   const int64_t n = h->n;
   const int64_t rows_per = std::max<int64_t>(1, (int64_t)(h->stage.n / (size_t)cols));
   for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
@@ -578,10 +724,30 @@ int upload_rows(hb_handle* h, const double* in, int cols, float* dst) {
     CK(cudaMemcpyAsync(h->stage.p, in + r0 * cols, sizeof(double) * (size_t)rows * cols, cudaMemcpyHostToDevice,
                        h->stream));
     k_upload_rows<<<grid_for(rows * cols, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->stage.p, dst, h->inv_sort.p, r0,
-                                                                                      rows, cols);
+                                                                                      rows, cols, ld);
     CKL();
     CK(cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+// K x B tables are stored [B][KS]; the boundary wants them dense
+int download_table(hb_handle* h, const float* src, double* out) {
+  k_compact<<<(h->B * h->K + 255) / 256, 256, 0, h->stream>>>(src, h->tmpT.p, h->B, h->K, h->KS);
+  CKL();
+  std::vector<float> tmp((size_t)h->B * h->K);
+  CK(cudaMemcpyAsync(tmp.data(), h->tmpT.p, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < tmp.size(); ++i) out[i] = (double)tmp[i];
+  return 0;
+}
+int upload_table(hb_handle* h, const double* in, float* dst) {
+  std::vector<float> tmp((size_t)h->B * h->K);
+  for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (float)in[i];
+  CK(cudaMemcpyAsync(h->tmpT.p, tmp.data(), sizeof(float) * tmp.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)h->B * h->KS, h->stream));
+  k_expand<<<(h->B * h->K + 255) / 256, 256, 0, h->stream>>>(h->tmpT.p, dst, h->B, h->K, h->KS);
+  CKL();
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 int download_small(hb_handle* h, const float* src, size_t count, double* out) {
@@ -722,6 +888,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   h->d = d;
   h->C = C;
   h->K = K;
+  h->KS = (K + 3) & ~3;
+  h->DS = (d + 3) & ~3;
   h->B_vec.assign(B_vec, B_vec + C);
   h->B = std::accumulate(h->B_vec.begin(), h->B_vec.end(), 0);
   const int B = h->B;
@@ -871,7 +1039,11 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     if (tstart[q + 1] == tstart[q]) t_chunk0[q] = (q + 1 < J) ? t_chunk0[q + 1] : h->nchunks - 1;
 
   // ---- device allocations
-  const size_t nK = (size_t)N * K, nd = (size_t)N * d;
+  const int KS = h->KS, DS = h->DS;
+  const size_t nK = (size_t)N * KS, nd = (size_t)N * DS, BK = (size_t)B * KS;
+  const int Tplan = std::max(1, (int)h->max_iter_kmeans);
+  h->use_v2 = (KS <= 256) && (J <= 8192) && (getenv("HB_UPDATE_V1") == nullptr);
+  h->plan_rounds = Tplan;
   CK(h->Zo.alloc(nd));
   CK(h->Zc.alloc(nd));
   CK(h->U.alloc(nK));
@@ -882,11 +1054,12 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->Pr_b.alloc(B));
   CK(h->N_b.alloc(B));
   CK(h->lambda.alloc(B + 1));
-  CK(h->O.alloc((size_t)B * K));
-  CK(h->E.alloc((size_t)B * K));
-  CK(h->P.alloc((size_t)B * K));
-  CK(h->Oacc.alloc((size_t)B * K + K));
-  CK(h->acc.alloc(4 * ((size_t)B * K + K)));
+  CK(h->O.alloc(BK));
+  CK(h->E.alloc(BK));
+  CK(h->P.alloc(BK));
+  CK(h->tmpT.alloc((size_t)B * K));
+  CK(h->Oacc.alloc(BK + KS));
+  CK(h->acc.alloc(4 * (BK + KS)));
   CK(h->S.alloc((size_t)J * K * (d + 1)));
   CK(h->V.alloc((size_t)J * K * d));
   CK(h->Wfull.alloc((size_t)K * (B + 1) * d));
@@ -905,19 +1078,33 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tile_tuple.alloc(h->ntiles));
   CK(h->chunk_start.alloc(h->nchunks + 1));
   CK(h->tuple_chunk0.alloc(J));
-  CK(h->blk_of.alloc(N));
-  CK(h->order.alloc(N));
+  CK(h->blk_of.alloc((size_t)Tplan * N));
+  CK(h->order.alloc((size_t)Tplan * N));
   CK(h->H.alloc((size_t)h->nb * h->nchunks));
-  CK(h->seg_start.alloc((size_t)h->nb * J + 1));
-  CK(h->tile_base.alloc((size_t)h->nb * J + 1));
+  CK(h->seg_start.alloc((size_t)Tplan * ((size_t)h->nb * J + 1)));
+  CK(h->tile_base.alloc((size_t)Tplan * ((size_t)h->nb * J + 1)));
+  if (h->use_v2) {
+    CK(h->ring.alloc(4 * BK));
+    CK(h->acc2.alloc(2 * (BK + KS) * ((size_t)Tplan * h->nb + 2)));
+    CK(h->Psave.alloc(2 * (size_t)h->nb * BK));
+    CK(h->OEend.alloc((size_t)Tplan * 2 * BK));
+    CK(h->obj2.alloc(2 * (size_t)Tplan));
+    CK(h->bar.alloc(2));
+    CK(cudaMemsetAsync(h->bar.p, 0, 2 * sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->Psave.p, 0, sizeof(float) * 2 * (size_t)h->nb * BK, h->stream));
+    CK(cudaMemsetAsync(h->ring.p, 0, sizeof(float) * 4 * BK, h->stream));
+  }
   CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
-  CK(cudaMemsetAsync(h->O.p, 0, sizeof(float) * (size_t)B * K, h->stream));
-  CK(cudaMemsetAsync(h->E.p, 0, sizeof(float) * (size_t)B * K, h->stream));
+  CK(cudaMemsetAsync(h->O.p, 0, sizeof(float) * BK, h->stream));
+  CK(cudaMemsetAsync(h->E.p, 0, sizeof(float) * BK, h->stream));
   CK(cudaMemsetAsync(h->Wfull.p, 0, sizeof(float) * (size_t)K * (B + 1) * d, h->stream));
   CK(cudaMemsetAsync(h->skipped.p, 0, sizeof(int) * K, h->stream));
   CK(cudaMemsetAsync(h->R.p, 0, sizeof(float) * nK, h->stream));
-  CK(cudaMemsetAsync(h->U.p, 0, sizeof(float) * nK, h->stream));
+  CK(cudaMemsetAsync(h->Zo.p, 0, sizeof(float) * nd, h->stream));
+  CK(cudaMemsetAsync(h->Zc.p, 0, sizeof(float) * nd, h->stream));
+  k_fill_f<<<grid_for((int64_t)nK, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->U.p, (int64_t)nK, U_PAD);
+  CKL();
   CK(cudaMemsetAsync(h->Y.p, 0, sizeof(float) * (size_t)K * d, h->stream));
 #define UP(buf, vec) CK(cudaMemcpyAsync(h->buf.p, (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, h->stream))
   UP(sort_perm, h->sort_perm_h);
@@ -951,8 +1138,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   }
 #undef UP
   // Z: double -> float, into tuple-sorted order (harmony.cpp:41); Z_corr = normalise(Z_orig) (:42)
-  TRY(upload_rows(h, Z, d, h->Zo.p));
-  k_normalise_rows<<<grid_for(N * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->Zo.p, h->Zc.p, N, d);
+  TRY(upload_rows(h, Z, d, h->DS, h->Zo.p));
+  k_normalise_rows<<<grid_for(N * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->Zo.p, h->Zc.p, N, d, h->DS);
   CKL();
   CK(cudaStreamSynchronize(h->stream));
   h->ran_setup = true;
@@ -966,13 +1153,30 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
   if (!Y0) return fail(h, 7, "native k-means initialisation is not available in this build; pass Y0");
   // Y = normalise(kmeans_centers(..)) (harmony.cpp:133-136)
   TRY(upload_small(h, Y0, (size_t)h->K * h->d, h->Y.p));
-  k_normalise_rows<<<grid_for((int64_t)h->K * 32, 256, 64), 256, 0, h->stream>>>(h->Y.p, h->Y.p, h->K, h->d);
+  k_normalise_rows<<<grid_for((int64_t)h->K * 32, 256, 64), 256, 0, h->stream>>>(h->Y.p, h->Y.p, h->K, h->d, h->d);
   CKL();
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
   TRY(run_assign(h, false));
   TRY(push_objective(h));                       // compute_objective() (:152)
   h->harmony_slots.push_back(h->obj_count - 1);  // objective_harmony.push_back (:153)
   h->ran_init = true;
+  return 0;
+}
+
+int ensure_plan_rounds(hb_handle* h, int T) {
+  if (T <= h->plan_rounds) return 0;
+  const size_t BK = (size_t)h->B * h->KS;
+  const size_t S1 = (size_t)h->nb * h->J + 1;
+  CK(h->blk_of.alloc((size_t)T * h->n));
+  CK(h->order.alloc((size_t)T * h->n));
+  CK(h->seg_start.alloc((size_t)T * S1));
+  CK(h->tile_base.alloc((size_t)T * S1));
+  if (h->use_v2) {
+    CK(h->acc2.alloc(2 * (BK + h->KS) * ((size_t)T * h->nb + 2)));
+    CK(h->OEend.alloc((size_t)T * 2 * BK));
+    CK(h->obj2.alloc(2 * (size_t)T));
+  }
+  h->plan_rounds = T;
   return 0;
 }
 
@@ -985,23 +1189,50 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
     TRY(run_assign(h, true));
     CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));  // the cold start does not evaluate the objective
   }
+  if (T > 31 && h->use_v2) return fail(h, 2, "max_iter_kmeans > 31 is not supported");
+  TRY(ensure_plan_rounds(h, (int)std::max(1u, T)));
   if (update_orders && T > 0) {
     size_t cnt = (size_t)T * (size_t)h->N_global;
     if (h->perms_d.n < cnt) CK(h->perms_d.alloc(cnt));
     CK(cudaMemcpyAsync(h->perms_d.p, update_orders, sizeof(int64_t) * cnt, cudaMemcpyHostToDevice, h->stream));
   }
-  unsigned iter;
-  for (iter = 0; iter < T; iter++) {
-    if (h->abort_cb && h->abort_cb(h->abort_user)) return -1;  // Progress::check_abort (:233)
-    TRY(build_plan(h, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr));
-    TRY(run_update_R(h));   // :241
-    TRY(push_objective(h));  // :248
-    if (iter > h->window_size) {  // :250-256
-      int conv = 0;
-      TRY(check_convergence_host(h, 0, &conv));
-      if (conv) {
-        iter++;
-        break;
+  if (h->abort_cb && h->abort_cb(h->abort_user)) return -1;  // Progress::check_abort (:233)
+  unsigned iter = 0;
+  if (h->use_v2) {
+    // all T update orders are drawn up front (they do not depend on the data), then the rounds run in
+    // chunks: [0, window_size + 2) in one launch, afterwards one round per launch (convergence checks)
+    for (unsigned t = 0; t < T; ++t)
+      TRY(build_plan(h, (int)t, update_orders ? h->perms_d.p + (size_t)t * (size_t)h->N_global : nullptr));
+    if (T > 0) TRY(upd_begin_call(h, (int)T));
+    unsigned t0 = 0;
+    while (t0 < T) {
+      unsigned t1 = (t0 == 0) ? std::min(T, h->window_size + 2) : t0 + 1;
+      unsigned mask = 0;
+      for (unsigned t = t0; t < t1; ++t)
+        if (t == T - 1 || t > h->window_size) mask |= 1u << t;  // rounds after which cluster_cpp may stop
+      if (t0 > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
+      TRY(run_update_v2(h, (int)T, (int)t0, (int)t1, mask));
+      iter = t1;
+      if (t1 - 1 > h->window_size) {  // :250-256
+        int conv = 0;
+        TRY(check_convergence_host(h, 0, &conv));
+        if (conv) break;
+      }
+      t0 = t1;
+    }
+  } else {
+    for (iter = 0; iter < T; iter++) {
+      if (iter > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
+      TRY(build_plan(h, 0, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr));
+      TRY(run_update_R_v1(h, 0));  // :241
+      TRY(push_objective(h));      // :248
+      if (iter > h->window_size) {  // :250-256
+        int conv = 0;
+        TRY(check_convergence_host(h, 0, &conv));
+        if (conv) {
+          iter++;
+          break;
+        }
       }
     }
   }
@@ -1034,7 +1265,7 @@ int hb_compute_objective(hb_handle* h) {
   CK(cudaSetDevice(h->device));
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
   k_objective_cells<<<grid_for(h->n * 32, ROW_THREADS, h->num_sms * 8), ROW_THREADS, 0, h->stream>>>(
-      h->R.p, h->U.p, h->sigma.p, h->n, h->K, h->obj_acc.p);
+      h->R.p, h->U.p, h->sigma.p, h->n, h->K, h->KS, h->obj_acc.p);
   CKL();
   return push_objective(h);
 }
@@ -1065,19 +1296,19 @@ int hb_get_field(hb_handle* h, int field, double* out) {
   CK(cudaSetDevice(h->device));
   const int K = h->K, B = h->B, d = h->d;
   switch (field) {
-    case HB_Z_CORR: return download_rows(h, h->Zc.p, d, out);
-    case HB_Z_ORIG: return download_rows(h, h->Zo.p, d, out);
-    case HB_R: return download_rows(h, h->R.p, K, out);
+    case HB_Z_CORR: return download_rows(h, h->Zc.p, d, h->DS, out);
+    case HB_Z_ORIG: return download_rows(h, h->Zo.p, d, h->DS, out);
+    case HB_R: return download_rows(h, h->R.p, K, h->KS, out);
     case HB_Y: return download_small(h, h->Y.p, (size_t)K * d, out);
-    case HB_O: return download_small(h, h->O.p, (size_t)K * B, out);
-    case HB_E: return download_small(h, h->E.p, (size_t)K * B, out);
+    case HB_O: return download_table(h, h->O.p, out);
+    case HB_E: return download_table(h, h->E.p, out);
     case HB_PR_B: return download_small(h, h->Pr_b.p, B, out);
     case HB_THETA: return download_small(h, h->theta.p, B, out);
     case HB_SIGMA: return download_small(h, h->sigma.p, K, out);
     case HB_LAMBDA_VEC: return download_small(h, h->lambda.p, B + 1, out);
     case HB_LAMBDA: {  // getLambda, harmony.cpp:657-669: K x (B+1) column-major
       std::vector<double> E((size_t)K * B), lam(B + 1);
-      TRY(download_small(h, h->E.p, (size_t)K * B, E.data()));
+      TRY(download_table(h, h->E.p, E.data()));
       TRY(download_small(h, h->lambda.p, B + 1, lam.data()));
       for (int k = 0; k < K; ++k) {
         out[k] = h->lambda_estimation ? 0.0 : lam[0];
@@ -1111,11 +1342,11 @@ int hb_set_field(hb_handle* h, int field, const double* in) {
   CK(cudaSetDevice(h->device));
   const int K = h->K, B = h->B, d = h->d;
   switch (field) {
-    case HB_Z_CORR: return upload_rows(h, in, d, h->Zc.p);
-    case HB_R: return upload_rows(h, in, K, h->R.p);
+    case HB_Z_CORR: return upload_rows(h, in, d, h->DS, h->Zc.p);
+    case HB_R: return upload_rows(h, in, K, h->KS, h->R.p);
     case HB_Y: return upload_small(h, in, (size_t)K * d, h->Y.p);
-    case HB_O: return upload_small(h, in, (size_t)K * B, h->O.p);
-    case HB_E: return upload_small(h, in, (size_t)K * B, h->E.p);
+    case HB_O: return upload_table(h, in, h->O.p);
+    case HB_E: return upload_table(h, in, h->E.p);
     case HB_THETA: return upload_small(h, in, B, h->theta.p);
     case HB_SIGMA: return upload_small(h, in, K, h->sigma.p);
     case HB_LAMBDA_VEC:

@@ -24,24 +24,24 @@ constexpr int NWARP = ROW_THREADS / 32;
 // dst[dst_row[r0 + r]][c] = (float)src[r][c]   (double -> float conversion of harmony.cpp:41 fused
 // with the scatter into tuple-sorted order)
 __global__ void k_upload_rows(const double* __restrict__ src, float* __restrict__ dst,
-                              const int* __restrict__ dst_row, int64_t r0, int64_t rows, int cols) {
+                              const int* __restrict__ dst_row, int64_t r0, int64_t rows, int cols, int ld) {
   int64_t total = rows * cols;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx / cols;
     int c = (int)(idx - r * cols);
-    dst[(int64_t)dst_row[r0 + r] * cols + c] = (float)src[idx];
+    dst[(int64_t)dst_row[r0 + r] * ld + c] = (float)src[idx];
   }
 }
 // out[r][c] = (double) src[src_row[r0 + r]][c]   (conv_to<RMAT>::from of harmony.cpp:640-650 + un-sort)
 __global__ void k_download_rows(const float* __restrict__ src, double* __restrict__ out,
-                                const int* __restrict__ src_row, int64_t r0, int64_t rows, int cols) {
+                                const int* __restrict__ src_row, int64_t r0, int64_t rows, int cols, int ld) {
   int64_t total = rows * cols;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx / cols;
     int c = (int)(idx - r * cols);
-    out[idx] = (double)src[(int64_t)src_row[r0 + r] * cols + c];
+    out[idx] = (double)src[(int64_t)src_row[r0 + r] * ld + c];
   }
 }
 __global__ void k_f2d(const float* __restrict__ src, double* __restrict__ out, int64_t n) {
@@ -52,6 +52,18 @@ __global__ void k_d2f(const double* __restrict__ src, float* __restrict__ out, i
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (float)src[i];
 }
+__global__ void k_fill_f(float* __restrict__ out, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+// compact a padded [rows][ld] table into [rows][cols]
+__global__ void k_compact(const float* __restrict__ src, float* __restrict__ out, int rows, int cols, int ld) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rows * cols) out[idx] = src[(idx / cols) * ld + (idx % cols)];
+}
+__global__ void k_expand(const float* __restrict__ src, float* __restrict__ out, int rows, int cols, int ld) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rows * cols) out[(idx / cols) * ld + (idx % cols)] = src[idx];
+}
 __global__ void k_copy_f(const float* __restrict__ src, float* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = src[i];
@@ -59,12 +71,12 @@ __global__ void k_copy_f(const float* __restrict__ src, float* __restrict__ out,
 
 // arma::normalise(X, 2, 0) on the rows of X[n][d] (= columns of the reference's d x N matrix); a zero
 // norm divides by 1.  One warp per row.  dst may alias src.
-__global__ void k_normalise_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int d) {
+__global__ void k_normalise_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int d, int ld) {
   int lane = threadIdx.x & 31;
   int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = w; r < n; r += nw) {
-    const float* x = src + r * d;
+    const float* x = src + r * ld;
     float s = 0.f;
     for (int c = lane; c < d; c += 32) {
       float v = x[c];
@@ -73,7 +85,7 @@ __global__ void k_normalise_rows(const float* __restrict__ src, float* __restric
     s = warp_sum(s);
     float nrm = sqrtf(s);
     if (nrm == 0.f) nrm = 1.f;
-    for (int c = lane; c < d; c += 32) dst[r * d + c] = x[c] / nrm;
+    for (int c = lane; c < d; c += 32) dst[r * ld + c] = x[c] / nrm;
   }
 }
 
@@ -98,6 +110,7 @@ struct AssignArgs {
   float* rs_acc;            // [K]
   double* obj_acc;          // [0] = sum R*dist, [1] = sum sigma R log R
   int ntiles, d, K, C, KP;  // KP = K rounded up to a multiple of 64
+  int DS, KS;               // row strides of Z and of U/R/O (multiples of 4 floats)
   int normalise;
 };
 
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) k_assign(AssignArgs a) {
     // ---- load (+ normalise) the Z tile into Zs[cell][dd]
     for (int r = warp; r < TM; r += NWARP) {
       if (r < len) {
-        float* zrow = a.Zc + (size_t)(cell0 + r) * d;
+        float* zrow = a.Zc + (size_t)(cell0 + r) * a.DS;
         float nrm = 1.f;
         if (a.normalise) {
           float s = 0.f;
@@ -222,8 +235,8 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) k_assign(AssignArgs a) {
         int k = lane + 32 * qq;
         if (k < K) {
           float rv = e[qq] / s;  // R.each_row() /= sum(R, 0): no zero guard in the reference
-          a.U[row * K + k] = u[qq];
-          a.R[row * K + k] = rv;
+          a.U[row * a.KS + k] = u[qq];
+          a.R[row * a.KS + k] = rv;
           cs[qq] += rv;
           okd += rv * dist[qq];
           if (rv > 0.f) oent += sig[k] * rv * (u[qq] - ls);
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) k_assign(AssignArgs a) {
 #pragma unroll
       for (int w = 0; w < NWARP; ++w) t += part[w * KP + k];
       atomicAdd(a.rs_acc + k, t);
-      for (int c = 0; c < a.C; ++c) atomicAdd(a.O_acc + (size_t)a.tuple_levels[q * a.C + c] * K + k, t);
+      for (int c = 0; c < a.C; ++c) atomicAdd(a.O_acc + (size_t)a.tuple_levels[q * a.C + c] * a.KS + k, t);
     }
   }
   okd = warp_sum(okd);
@@ -255,12 +268,12 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) k_assign(AssignArgs a) {
 // E = sum(R,1) * Pr_b^T (harmony.cpp:149,226) and O from the accumulators.
 __global__ void k_assign_finalize(const float* __restrict__ O_acc, const float* __restrict__ rs_acc,
                                   const float* __restrict__ Pr_b, float* __restrict__ O, float* __restrict__ E,
-                                  int B, int K) {
+                                  int B, int K, int KS) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < B * K) {
-    int b = idx / K, k = idx - b * K;
-    O[idx] = O_acc[idx];
-    E[idx] = rs_acc[k] * Pr_b[b];
+  if (idx < B * KS) {
+    int b = idx / KS, k = idx - b * KS;
+    O[idx] = (k < K) ? O_acc[idx] : 0.f;
+    E[idx] = (k < K) ? rs_acc[k] * Pr_b[b] : 0.f;
   }
 }
 
@@ -418,7 +431,7 @@ struct StepArgs {
   float* acc_O;             // [B][K] column sums per level (rem_j or add_j)
   float* acc_rs;            // [K]
   double* obj_acc;          // [2]
-  int blk, J, K, C, KP;
+  int blk, J, K, C, KP, KS;
 };
 
 // tile -> (segment, first position, length)
@@ -469,7 +482,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_colsum(StepArgs a) {
 #pragma unroll
       for (int qq = 0; qq < KQ; ++qq) {
         int k = lane + 32 * qq;
-        if (k < K) cs[qq] += a.R[row * K + k];
+        if (k < K) cs[qq] += a.R[row * a.KS + k];
       }
     }
 #pragma unroll
@@ -483,7 +496,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_colsum(StepArgs a) {
 #pragma unroll
       for (int w = 0; w < NWARP; ++w) s += part[w * KP + k];
       atomicAdd(a.acc_rs + k, s);
-      for (int c = 0; c < a.C; ++c) atomicAdd(a.acc_O + (size_t)a.tuple_levels[q * a.C + c] * K + k, s);
+      for (int c = 0; c < a.C; ++c) atomicAdd(a.acc_O + (size_t)a.tuple_levels[q * a.C + c] * a.KS + k, s);
     }
   }
 }
@@ -496,10 +509,11 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_colsum(StepArgs a) {
 __global__ void k_step_prepare(float* __restrict__ O, float* __restrict__ E, const float* __restrict__ add_O,
                                const float* __restrict__ add_rs, const float* __restrict__ rem_O,
                                const float* __restrict__ rem_rs, const float* __restrict__ Pr_b,
-                               const float* __restrict__ theta, float* __restrict__ P, int B, int K) {
+                               const float* __restrict__ theta, float* __restrict__ P, int B, int K, int KS) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * K) return;
-  int b = idx / K, k = idx - b * K;
+  if (idx >= B * KS) return;
+  int b = idx / KS, k = idx - b * KS;
+  if (k >= K) return;
   float o = O[idx], e = E[idx];
   if (add_O) {
     e += add_rs[k] * Pr_b[b];
@@ -535,7 +549,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_update(StepArgs a) {
     const int q = seg - a.blk * a.J;
     for (int k = tid; k < K; k += ROW_THREADS) {
       float s = 0.f;
-      for (int c = 0; c < a.C; ++c) s += a.P[(size_t)a.tuple_levels[q * a.C + c] * K + k];
+      for (int c = 0; c < a.C; ++c) s += a.P[(size_t)a.tuple_levels[q * a.C + c] * a.KS + k];
       Psum[k] = s;
       lP[k] = logf(s);
     }
@@ -551,7 +565,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_update(StepArgs a) {
       for (int qq = 0; qq < KQ; ++qq) {
         int k = lane + 32 * qq;
         if (k < K) {
-          u[qq] = ld_stream(a.U + row * K + k);
+          u[qq] = ld_stream(a.U + row * a.KS + k);
           e[qq] = expf(u[qq]) * Psum[k];
         } else {
           u[qq] = 0.f;
@@ -567,7 +581,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_update(StepArgs a) {
         int k = lane + 32 * qq;
         if (k < K) {
           float rv = e[qq] / sdiv;
-          st_stream(a.R + row * K + k, rv);
+          st_stream(a.R + row * a.KS + k, rv);
           cs[qq] += rv;
           okd += rv * (-sig[k] * u[qq]);
           if (rv > 0.f) oent += sig[k] * rv * (u[qq] + lP[k] - ls);
@@ -585,7 +599,7 @@ __global__ void __launch_bounds__(ROW_THREADS) k_block_update(StepArgs a) {
 #pragma unroll
       for (int w = 0; w < NWARP; ++w) s += part[w * KP + k];
       atomicAdd(a.acc_rs + k, s);
-      for (int c = 0; c < a.C; ++c) atomicAdd(a.acc_O + (size_t)a.tuple_levels[q * a.C + c] * K + k, s);
+      for (int c = 0; c < a.C; ++c) atomicAdd(a.acc_O + (size_t)a.tuple_levels[q * a.C + c] * a.KS + k, s);
     }
   }
   okd = warp_sum(okd);
@@ -603,11 +617,12 @@ __global__ void __launch_bounds__(256) k_objective_finalize(const float* __restr
                                                             const float* __restrict__ theta,
                                                             const float* __restrict__ sigma, double* obj_acc,
                                                             float* __restrict__ trace, int slot, int B, int K,
-                                                            double N_global, double cross_scale) {
+                                                            int KS, double N_global, double cross_scale) {
   __shared__ double red[8];
   double acc = 0.0;
-  for (int idx = threadIdx.x; idx < B * K; idx += blockDim.x) {
-    int b = idx / K, k = idx - b * K;
+  for (int idx = threadIdx.x; idx < B * KS; idx += blockDim.x) {
+    int b = idx / KS, k = idx - b * KS;
+    if (k >= K) continue;
     float o = O[idx], e = E[idx];
     float l = theta[b] * logf((o + e + 1.f) / ((2.f * e) + 1.f));
     acc += (double)(sigma[k] * l) * (double)o;
@@ -633,14 +648,14 @@ __global__ void __launch_bounds__(256) k_objective_finalize(const float* __restr
 // Standalone per-cell objective sums from the stored R and U (for hb_compute_objective).
 __global__ void __launch_bounds__(ROW_THREADS) k_objective_cells(const float* __restrict__ R, const float* __restrict__ U,
                                                                 const float* __restrict__ sigma, int64_t n, int K,
-                                                                double* obj_acc) {
+                                                                int KS, double* obj_acc) {
   const int lane = threadIdx.x & 31;
   int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   float okd = 0.f, oent = 0.f;
   for (int64_t r = w; r < n; r += nw) {
     for (int k = lane; k < K; k += 32) {
-      float rv = R[r * K + k], u = U[r * K + k], sg = sigma[k];
+      float rv = R[r * KS + k], u = U[r * KS + k], sg = sigma[k];
       okd += rv * (-sg * u);
       if (rv > 0.f) oent += sg * rv * logf(rv);
     }
@@ -667,6 +682,7 @@ struct StatsArgs {
   float* S;  // [J][K][d+1]
   int ntiles, d, K, KS;  // KS = clusters per K-slice (blockIdx.y)
   int tiles_per_cta;
+  int ldR, ldZ;          // row strides of R and Zo
 };
 
 __global__ void k_ridge_stats(StatsArgs a) {
@@ -717,12 +733,12 @@ __global__ void k_ridge_stats(StatsArgs a) {
     __syncthreads();
     for (int idx = tid; idx < TM * KSP; idx += nthr) {
       int r = idx / KSP, k = idx - r * KSP;
-      Rs[idx] = (r < len && k < ks) ? ld_stream(a.R + (size_t)(cell0 + r) * K + k0 + k) : 0.f;
+      Rs[idx] = (r < len && k < ks) ? ld_stream(a.R + (size_t)(cell0 + r) * a.ldR + k0 + k) : 0.f;
     }
     for (int idx = tid; idx < TM * DP; idx += nthr) {
       int r = idx / DP, c = idx - r * DP;
       float v = 0.f;
-      if (r < len) v = (c < d) ? ld_stream(a.Zo + (size_t)(cell0 + r) * d + c) : ((c == d) ? 1.f : 0.f);
+      if (r < len) v = (c < d) ? ld_stream(a.Zo + (size_t)(cell0 + r) * a.ldZ + c) : ((c == d) ? 1.f : 0.f);
       Zs[idx] = v;
     }
     __syncthreads();
@@ -762,7 +778,7 @@ struct SolveArgs {
   float* scratch;             // [K][ 2*M*M + M*d ]  (G | inv | s),  M = B+1
   int* iscratch;              // [K][ 2*B + J ]      (pos | keep | part)
   int* err_flag;
-  int J, K, B, C, d;
+  int J, K, B, C, d, KS;  // KS = row stride of O and E
   float alpha, cutoff;
 };
 
@@ -786,7 +802,7 @@ __global__ void __launch_bounds__(256) k_ridge_solve(SolveArgs a) {
   for (int c = tid; c < C; c += nt) cov_levels[c] = 0;
   __syncthreads();
   for (int b = tid; b < B; b += nt) {
-    int ov = ((a.O[(size_t)b * K + k] / a.N_b[b]) > a.cutoff) ? 1 : 0;
+    int ov = ((a.O[(size_t)b * a.KS + k] / a.N_b[b]) > a.cutoff) ? 1 : 0;
     over[b] = ov;
     if (ov) atomicAdd(&cov_levels[a.cov_of[b]], 1);
   }
@@ -858,7 +874,7 @@ __global__ void __launch_bounds__(256) k_ridge_solve(SolveArgs a) {
   // ---- + diag(lambda): lambda_0 = 0, lambda_b = alpha*E_kb (find_lambda_cpp) or the fixed vector
   for (int j = tid; j < m - 1; j += nt) {
     int b = keep[j];
-    float lam = a.lambda ? a.lambda[b + 1] : a.E[(size_t)b * K + k] * a.alpha;
+    float lam = a.lambda ? a.lambda[b + 1] : a.E[(size_t)b * a.KS + k] * a.alpha;
     G[(size_t)(j + 1) * m + (j + 1)] += lam;
   }
   if (tid == 0 && a.lambda) G[0] += a.lambda[0];
@@ -997,6 +1013,7 @@ struct ApplyArgs {
   const int* tile_len;
   const int* tile_tuple;
   int ntiles, d, K, tiles_per_cta;
+  int ldR, ldZ;
 };
 
 __global__ void k_ridge_apply(ApplyArgs a) {
@@ -1022,7 +1039,7 @@ __global__ void k_ridge_apply(ApplyArgs a) {
     }
     for (int idx = tid; idx < TM * KP4; idx += nthr) {
       int r = idx / KP4, k = idx - r * KP4;
-      Rs[idx] = (r < len && k < K) ? ld_stream(a.R + (size_t)(cell0 + r) * K + k) : 0.f;
+      Rs[idx] = (r < len && k < K) ? ld_stream(a.R + (size_t)(cell0 + r) * a.ldR + k) : 0.f;
     }
     __syncthreads();
     float acc[4][4];
@@ -1056,7 +1073,7 @@ __global__ void k_ridge_apply(ApplyArgs a) {
         for (int j = 0; j < 4; ++j) {
           int c = tx * 4 + j;
           if (c < d) {
-            size_t g = (size_t)(cell0 + r) * d + c;
+            size_t g = (size_t)(cell0 + r) * a.ldZ + c;
             a.Zc[g] = a.Zo[g] - acc[i][j];
           }
         }
