@@ -124,12 +124,17 @@ struct hb_handle {
   DevBuf<float> ring, acc2, Psave, OEend, tmpT;  // persistent update kernel state
   DevBuf<double> obj2;
   DevBuf<unsigned> bar;
+  DevBuf<long long> dbg;  // optional step-phase timestamps (HB_TRACE_STEPS=<cta>)
+  int dbg_cta = -1;
   int plan_rounds = 0;   // rounds the plan buffers hold
   bool use_v2 = true;
+  bool sigma_uniform = false;
+  float sigma0 = 0.f;
+  bool R_user_set = false;  // R was written through hb_set_field since the last assignment step
   int coop_grid = 0;
   DevBuf<double> obj_acc, stage;
   DevBuf<int> sort_perm, inv_sort, tuple_levels, cov_of_d, tile_cell0, tile_len, tile_tuple, chunk_start,
-      tuple_chunk0, blk_of, order, H, seg_start, tile_base, iscratch, skipped, err_flag;
+      tuple_chunk0, blk_of, order, prev_at, H, seg_start, tile_base, iscratch, skipped, err_flag;
   DevBuf<int64_t> perms_d;
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
@@ -296,6 +301,7 @@ int run_assign(hb_handle* h, bool normalise) {
     return 0;
   });
   TRY(st);
+  h->R_user_set = false;
   TRY(allreduce_f(h, h->Oacc.p, (size_t)B * KS + KS));
   k_assign_finalize<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * KS, h->Pr_b.p,
                                                                   h->O.p, h->E.p, B, K, KS);
@@ -398,7 +404,9 @@ int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, o
   CKL();
   k_scan_exclusive<<<1, 1024, 0, h->stream>>>(h->H.p, (int64_t)nb * nc, nullptr);
   CKL();
-  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(blk_of, h->chunk_start.p, nc, nb, h->H.p, order);
+  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(
+      blk_of, h->chunk_start.p, nc, nb, h->H.p, order, (t > 0) ? h->blk_of.p + (size_t)(t - 1) * n : nullptr,
+      h->use_v2 ? h->prev_at.p + (size_t)t * n : nullptr);
   CKL();
   k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
                                                                     seg_start, tile_base);
@@ -479,7 +487,7 @@ int run_update_R_v1(hb_handle* h, int t) {
 // ---- v2: persistent cooperative kernel over rounds [t0, t1) of this cluster_cpp call --------------
 int nv_for(int KS) {
   int nv = 1;
-  while (32 * nv < KS) nv <<= 1;
+  while (4 * UPD_LPR * nv < KS) nv <<= 1;
   return nv;
 }
 template <typename F>
@@ -488,13 +496,14 @@ int dispatch_nv(hb_handle* h, int KS, F&& f) {
     case 1: return f(std::integral_constant<int, 1>());
     case 2: return f(std::integral_constant<int, 2>());
     case 4: return f(std::integral_constant<int, 4>());
-    case 8: return f(std::integral_constant<int, 8>());
   }
   return fail(h, 2, "K = %d is not supported by the persistent update kernel", h->K);
 }
 size_t upd_smem_bytes(const hb_handle* h) {
-  return sizeof(float) * ((size_t)3 * h->KS + (size_t)UPD_WARPS * h->KS + (size_t)h->nb * h->KS) +
-         sizeof(int) * ((size_t)h->J + 1);
+  const size_t tabn = (size_t)std::max(2, h->nb) * h->KS;
+  const int nv = nv_for(h->KS);
+  const size_t rowbuf = (size_t)UPD_GWARPS * (upd_depth_upd(nv) + upd_depth_look(nv)) * UPD_RPW * h->KS;
+  return sizeof(float) * ((size_t)h->KS + 2 * (tabn + (size_t)UPD_GWARPS * h->KS + 2 * (size_t)UPD_STAGE + (size_t)((h->J + 8) & ~3)) + rowbuf);
 }
 UpdArgs make_upd_args(hb_handle* h, int T) {
   UpdArgs a;
@@ -502,7 +511,7 @@ UpdArgs make_upd_args(hb_handle* h, int T) {
   a.R = h->R.p;
   a.order = h->order.p;
   a.seg_start = h->seg_start.p;
-  a.blk_of = h->blk_of.p;
+  a.prev_at = h->prev_at.p;
   a.tuple_levels = h->tuple_levels.p;
   a.sigma = h->sigma.p;
   a.theta = h->theta.p;
@@ -521,7 +530,11 @@ UpdArgs make_upd_args(hb_handle* h, int T) {
   a.B = h->B;
   a.nb = h->nb;
   a.T = T;
-  a.first_round_from_R = 1;
+  a.first_round_from_R = h->R_user_set ? 1 : 0;
+  a.sigma_uniform = h->sigma_uniform ? 1 : 0;
+  a.sigma0 = h->sigma0;
+  a.dbg = (h->dbg_cta >= 0) ? h->dbg.p : nullptr;
+  a.dbg_cta = h->dbg_cta;
   return a;
 }
 // zero the per-step accumulators and seed ring[1] (= "O_{-1}") with the current tables
@@ -529,6 +542,7 @@ int upd_begin_call(hb_handle* h, int T) {
   const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
   CK(cudaMemsetAsync(h->acc2.p, 0, sizeof(float) * SL * ((size_t)T * h->nb + 2), h->stream));
   CK(cudaMemsetAsync(h->obj2.p, 0, sizeof(double) * 2 * (size_t)T, h->stream));
+  CK(cudaMemsetAsync(h->bar.p, 0, sizeof(unsigned) * 2 * ((size_t)T * h->nb + 2), h->stream));
   CK(cudaMemcpyAsync(h->ring.p + 2 * BK, h->O.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->ring.p + 3 * BK, h->E.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   return 0;
@@ -583,6 +597,25 @@ int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
       TRY(upd_launch(h, a, false));
     }
     TRY(allreduce_f(h, h->acc2.p + (size_t)(t1 * nb + 1) * SL, SL));  // slot(S): add_{S-1} (+ look-ahead rem_S)
+  }
+  if (h->dbg_cta >= 0 && h->world <= 1) {
+    const int ns = (t1 - t0) * nb;
+    std::vector<long long> st((size_t)(ns + 1) * 16);
+    CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    static int dumped = 0;
+    if (dumped++ == 3) {
+      FILE* f = fopen("gpurun_out/step_trace.txt", "w");
+      if (f) {
+        for (int s = 0; s <= ns; ++s) {
+          fprintf(f, "%d", s - 1);
+          for (int g = 0; g < 2; ++g)
+            for (int k = 0; k < 8; ++k) fprintf(f, " %lld", st[((size_t)s * 2 + g) * 8 + k]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
   }
   // tables at the end of round t1-1 -> O, E (the chain itself continues from the ring)
   {
@@ -1080,6 +1113,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tuple_chunk0.alloc(J));
   CK(h->blk_of.alloc((size_t)Tplan * N));
   CK(h->order.alloc((size_t)Tplan * N));
+  CK(h->prev_at.alloc((size_t)Tplan * N));
   CK(h->H.alloc((size_t)h->nb * h->nchunks));
   CK(h->seg_start.alloc((size_t)Tplan * ((size_t)h->nb * J + 1)));
   CK(h->tile_base.alloc((size_t)Tplan * ((size_t)h->nb * J + 1)));
@@ -1089,8 +1123,12 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->Psave.alloc(2 * (size_t)h->nb * BK));
     CK(h->OEend.alloc((size_t)Tplan * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)Tplan));
-    CK(h->bar.alloc(2));
-    CK(cudaMemsetAsync(h->bar.p, 0, 2 * sizeof(unsigned), h->stream));
+    CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));
+    if (const char* e = getenv("HB_TRACE_STEPS")) {
+      h->dbg_cta = atoi(e);
+      CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));
+      CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * (size_t)(32 * h->nb + 2) * 16, h->stream));
+    }
     CK(cudaMemsetAsync(h->Psave.p, 0, sizeof(float) * 2 * (size_t)h->nb * BK, h->stream));
     CK(cudaMemsetAsync(h->ring.p, 0, sizeof(float) * 4 * BK, h->stream));
   }
@@ -1119,6 +1157,9 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   {
     std::vector<float> f(K);
     for (int k = 0; k < K; ++k) f[k] = (float)sigma[k];
+    h->sigma0 = f[0];
+    h->sigma_uniform = true;
+    for (int k = 1; k < K; ++k) h->sigma_uniform = h->sigma_uniform && (f[k] == f[0]);
     UP(sigma, f);
     f.resize(B);
     for (int b = 0; b < B; ++b) f[b] = (float)theta[b];
@@ -1169,12 +1210,14 @@ int ensure_plan_rounds(hb_handle* h, int T) {
   const size_t S1 = (size_t)h->nb * h->J + 1;
   CK(h->blk_of.alloc((size_t)T * h->n));
   CK(h->order.alloc((size_t)T * h->n));
+  CK(h->prev_at.alloc((size_t)T * h->n));
   CK(h->seg_start.alloc((size_t)T * S1));
   CK(h->tile_base.alloc((size_t)T * S1));
   if (h->use_v2) {
     CK(h->acc2.alloc(2 * (BK + h->KS) * ((size_t)T * h->nb + 2)));
     CK(h->OEend.alloc((size_t)T * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)T));
+    CK(h->bar.alloc(2 * ((size_t)T * h->nb + 2)));
   }
   h->plan_rounds = T;
   return 0;
@@ -1236,6 +1279,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
       }
     }
   }
+  if (T > 0) h->R_user_set = false;
   if (update_orders) TRY(check_err_flag(h));
   h->kmeans_rounds.push_back((int)iter);         // :259
   h->harmony_slots.push_back(h->obj_count - 1);  // :260
@@ -1343,12 +1387,18 @@ int hb_set_field(hb_handle* h, int field, const double* in) {
   const int K = h->K, B = h->B, d = h->d;
   switch (field) {
     case HB_Z_CORR: return upload_rows(h, in, d, h->DS, h->Zc.p);
-    case HB_R: return upload_rows(h, in, K, h->KS, h->R.p);
+    case HB_R:
+      h->R_user_set = true;
+      return upload_rows(h, in, K, h->KS, h->R.p);
     case HB_Y: return upload_small(h, in, (size_t)K * d, h->Y.p);
     case HB_O: return upload_table(h, in, h->O.p);
     case HB_E: return upload_table(h, in, h->E.p);
     case HB_THETA: return upload_small(h, in, B, h->theta.p);
-    case HB_SIGMA: return upload_small(h, in, K, h->sigma.p);
+    case HB_SIGMA:
+      h->sigma0 = (float)in[0];
+      h->sigma_uniform = true;
+      for (int k = 1; k < K; ++k) h->sigma_uniform = h->sigma_uniform && ((float)in[k] == (float)in[0]);
+      return upload_small(h, in, K, h->sigma.p);
     case HB_LAMBDA_VEC:
       h->lambda_estimation = false;
       return upload_small(h, in, B + 1, h->lambda.p);

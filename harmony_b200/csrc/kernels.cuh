@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data,
 }
 // Stable scatter: order[offset(blk, chunk) + rank] = cell, cells of a chunk visited in ascending order.
 __global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __restrict__ chunk_start, int nchunks,
-                               int nb, const int* __restrict__ Hoff, int* __restrict__ order) {
+                               int nb, const int* __restrict__ Hoff, int* __restrict__ order,
+                               const int* __restrict__ blk_prev, int* __restrict__ prev_at) {
   extern __shared__ int sh[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cur = sh + warp * nb;
@@ -387,7 +388,10 @@ __global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __rest
       cur[b] = start + __popc(m);
     }
     start = __shfl_sync(0xffffffffu, start, leader);
-    if (act) order[start + rank] = s;
+    if (act) {
+      order[start + rank] = s;
+      if (prev_at) prev_at[start + rank] = blk_prev ? blk_prev[s] : 0;
+    }
     __syncwarp();
   }
 }
