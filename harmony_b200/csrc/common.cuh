@@ -5,6 +5,10 @@
 
 #define HB_WARP 32
 
+namespace hb {
+constexpr float U_PAD = -1.0e30f;  // logit stored in the padding columns of U (exp -> 0)
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

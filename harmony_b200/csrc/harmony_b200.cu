@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "update_kernel.cuh"
+#include "assign_tc.cuh"
 
 namespace {
 
@@ -136,6 +137,9 @@ struct hb_handle {
   DevBuf<int> sort_perm, inv_sort, tuple_levels, cov_of_d, tile_cell0, tile_len, tile_tuple, chunk_start,
       tuple_chunk0, blk_of, order, prev_at, H, seg_start, tile_base, iscratch, skipped, err_flag;
   DevBuf<int64_t> perms_d;
+  DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
+  int tc_ntiles = 0;
+  bool use_tc_assign = false;
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
@@ -286,6 +290,62 @@ int run_assign(hb_handle* h, bool normalise) {
   a.DS = h->DS;
   a.KS = KS;
   a.normalise = normalise ? 1 : 0;
+  if (h->use_tc_assign) {
+    AssignTcArgs t;
+    t.Zc = a.Zc;
+    t.Y = a.Y;
+    t.sigma = a.sigma;
+    t.U = a.U;
+    t.R = a.R;
+    t.tile_cell0 = h->tc_cell0.p;
+    t.tile_len = h->tc_len.p;
+    t.tile_tuple = h->tc_tuple.p;
+    t.tuple_levels = a.tuple_levels;
+    t.O_acc = a.O_acc;
+    t.rs_acc = a.rs_acc;
+    t.obj_acc = a.obj_acc;
+    t.ntiles = h->tc_ntiles;
+    t.d = d;
+    t.K = K;
+    t.C = h->C;
+    t.DS = h->DS;
+    t.KS = KS;
+    t.KD = (d + 7) & ~7;
+    t.NP = (K + 15) & ~15;
+    t.normalise = a.normalise;
+    t.dbg = nullptr;
+    static int trace_calls = 0;
+    const bool tracing = getenv("HB_TRACE_ASSIGN") != nullptr && (++trace_calls == 4);
+    if (tracing) {
+      if (h->dbg.n < 64 * 24) CK(h->dbg.alloc(64 * 24));
+      CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 64 * 24, h->stream));
+      t.dbg = h->dbg.p;
+    }
+    const size_t smem_tc = assign_tc_smem_bytes(t.KD, t.NP, KS);
+    CK(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+    const int grid_tc = std::max(1, std::min(h->tc_ntiles, h->num_sms));
+    k_assign_tc<<<grid_tc, TC_THREADS, smem_tc, h->stream>>>(t);
+    CKL();
+    if (tracing) {
+      std::vector<long long> st(64 * 24);
+      CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (FILE* f = fopen("gpurun_out/assign_trace.txt", "w")) {
+        for (int i = 0; i < 64; ++i) {
+          fprintf(f, "%d", i);
+          for (int k = 0; k < 24; ++k) fprintf(f, " %lld", st[(size_t)i * 24 + k]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
+    h->R_user_set = false;
+    TRY(allreduce_f(h, h->Oacc.p, (size_t)B * KS + KS));
+    k_assign_finalize<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * KS, h->Pr_b.p,
+                                                                    h->O.p, h->E.p, B, K, KS);
+    CKL();
+    return 0;
+  }
   size_t smem = sizeof(float) * ((size_t)DP4 * KP + (size_t)TM * DP4 + (size_t)TM * (KP + 4) + KP + (size_t)NWARP * KP);
   if (smem > 227 * 1024) return fail(h, 2, "K*d too large for the assignment kernel (needs %zu B shared memory)", smem);
   int st = dispatch_kq(h, K, [&](auto kq) -> int {
@@ -1063,6 +1123,14 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     t_chunk0[q] = (int)c_start.size();
     for (int64_t s = tstart[q]; s < tstart[q + 1]; s += CHUNK) c_start.push_back((int)s);
   }
+  std::vector<int> tc0, tcl, tct;  // 128-cell tiles for the tensor-core kernels
+  for (int q = 0; q < J; ++q)
+    for (int64_t s2 = tstart[q]; s2 < tstart[q + 1]; s2 += TC_TM) {
+      tc0.push_back((int)s2);
+      tcl.push_back((int)std::min<int64_t>(TC_TM, tstart[q + 1] - s2));
+      tct.push_back(q);
+    }
+  h->tc_ntiles = (int)tc0.size();
   c_start.push_back((int)N);  // start of the trailing empty chunk
   c_start.push_back((int)N);  // and its end
   h->ntiles = (int)t_cell0.size();
@@ -1109,6 +1177,11 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tile_cell0.alloc(h->ntiles));
   CK(h->tile_len.alloc(h->ntiles));
   CK(h->tile_tuple.alloc(h->ntiles));
+  CK(h->tc_cell0.alloc(h->tc_ntiles));
+  CK(h->tc_len.alloc(h->tc_ntiles));
+  CK(h->tc_tuple.alloc(h->tc_ntiles));
+  h->use_tc_assign = (h->DS <= 4 * TC_DS4MAX) && (KS <= 256) &&
+                     assign_tc_smem_bytes((d + 7) & ~7, (K + 15) & ~15, KS) <= 227 * 1024 && (getenv("HB_ASSIGN_FFMA") == nullptr);
   CK(h->chunk_start.alloc(h->nchunks + 1));
   CK(h->tuple_chunk0.alloc(J));
   CK(h->blk_of.alloc((size_t)Tplan * N));
@@ -1152,6 +1225,9 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   UP(tile_cell0, t_cell0);
   UP(tile_len, t_len);
   UP(tile_tuple, t_tuple);
+  UP(tc_cell0, tc0);
+  UP(tc_len, tcl);
+  UP(tc_tuple, tct);
   UP(chunk_start, c_start);
   UP(tuple_chunk0, t_chunk0);
   {

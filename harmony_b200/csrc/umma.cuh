@@ -1,0 +1,124 @@
+// umma.cuh — thin inline-PTX wrappers for the sm_100a tensor-core path: tcgen05.mma (kind::tf32) with
+// shared-memory operand descriptors, TMEM allocation / loads, mbarriers.  Layout facts follow the PTX ISA
+// "tcgen05" chapter; the field positions were cross-checked against the CUTLASS headers shipped in this
+// image (cute/arch/mma_sm100_desc.hpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM ---------------------------------------------------------------------------------------
+// One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *dst (shared).
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i), columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors --------------------------------------------------------------------------------
+// Shared-memory operand descriptor, no swizzle.  Canonical K-major layout (units of 16 bytes):
+//   ((8, m), 2) : ((1, SBO), LBO)   -> 8 rows x 16 B form a contiguous 128-byte core matrix; the next 8-row
+// group is SBO bytes further, the next 16-byte chunk along K is LBO bytes further.  For MN-major operands
+// the roles are: ((1, n), (8, k)) : ((X, SBO), (1, LBO)) (see make_desc_mn below).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+// Instruction descriptor of tcgen05.mma.kind::tf32, fp32 accumulate, dense.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                      // c_format  = F32
+         | (2u << 7)                    // a_format  = TF32
+         | (2u << 10)                   // b_format  = TF32
+         | ((uint32_t)a_mn_major << 15) // 0 = K-major
+         | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17)
+         | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.  accumulate = 0 overwrites D.
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All previously issued MMAs of this thread arrive on the mbarrier when they complete.
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// tf32 split for 3xTF32 (error-compensated fp32-grade products): x ~= hi + lo, both exactly representable
+// in tf32, so a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with ~2^-22 relative error per product.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = round_tf32(x);          // nearest tf32: |x - hi| <= 2^-12 |x|
+  lo = round_tf32(x - hi);     // the remainder (exact in fp32) at tf32 precision
+}
+
+// 1-D bulk (TMA) copy shared -> global, completion tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until the sources of all committed bulk groups have been read (smem may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+}  // namespace umma

