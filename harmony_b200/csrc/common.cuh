@@ -64,3 +64,22 @@ __host__ __device__ __forceinline__ uint64_t hb_permute(uint64_t i, uint64_t n, 
   } while (x >= n);
   return x;
 }
+
+// Inverse of hb_permute: the cell that sits at position `pos`.
+__host__ __device__ __forceinline__ uint64_t hb_permute_inv(uint64_t pos, uint64_t n, int half_bits, uint64_t key) {
+  const uint64_t mask = (1ull << half_bits) - 1ull;
+  uint64_t x = pos;
+  do {
+    uint64_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+    for (int round = 5; round >= 0; --round) {
+      // forward round: (l, r) -> (r, l ^ f(r));  inverse: (l', r') -> (r' ^ f(l'), l')
+      uint64_t f = hb_mix64(l ^ (key + 0x632BE59BD9B4E019ull * (uint64_t)(round + 1))) & mask;
+      uint64_t pl = r ^ f;
+      r = l;
+      l = pl;
+    }
+    x = (l << half_bits) | r;
+  } while (x >= n);
+  return x;
+}

@@ -1267,9 +1267,37 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
   if (!h) return 1;
   if (!h->ran_setup) return fail(h, 3, "setup has not been run");
   CK(cudaSetDevice(h->device));
-  if (!Y0) return fail(h, 7, "native k-means initialisation is not available in this build; pass Y0");
-  // Y = normalise(kmeans_centers(..)) (harmony.cpp:133-136)
-  TRY(upload_small(h, Y0, (size_t)h->K * h->d, h->Y.p));
+  if (Y0) {
+    // Y = normalise(kmeans_centers(..)) (harmony.cpp:133-136), centroids injected by the caller
+    TRY(upload_small(h, Y0, (size_t)h->K * h->d, h->Y.p));
+  } else {
+    // native initialisation: K distinct random cells, then 10 Lloyd iterations (utils.cpp:53-64 runs
+    // 10 x arma::kmeans(.., keep_existing, 1)) on the cosine-normalised cells, sharded like everything else
+    const int K = h->K, d = h->d;
+    const size_t Kd = (size_t)K * d;
+    DevBuf<float> ysum;
+    CK(ysum.alloc(Kd + K));
+    CK(cudaMemsetAsync(h->Y.p, 0, sizeof(float) * Kd, h->stream));
+    const uint64_t key = hb_mix64(h->seed ^ 0x6b6d65616e73ull);
+    k_kmeans_seed<<<K, 64, 0, h->stream>>>(h->Zc.p, h->inv_sort.p, h->Y.p, K, d, h->DS, h->N_global, h->cell_offset, h->n,
+                                            h->half_bits, key);
+    CKL();
+    TRY(allreduce_f(h, h->Y.p, Kd));
+    const size_t smem = sizeof(float) * Kd;
+    if (smem > 200 * 1024) return fail(h, 2, "K*d too large for the native k-means initialisation; pass Y0");
+    CK(cudaFuncSetAttribute(k_kmeans_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int iter = 0; iter < 10; ++iter) {
+      CK(cudaMemsetAsync(ysum.p, 0, sizeof(float) * (Kd + K), h->stream));
+      k_kmeans_assign<<<grid_for(h->n, 128, h->num_sms * 4), 128, smem, h->stream>>>(h->Zc.p, h->Y.p, ysum.p, ysum.p + Kd,
+                                                                                       h->n, K, d, h->DS);
+      CKL();
+      TRY(allreduce_f(h, ysum.p, Kd + K));
+      k_kmeans_update<<<(int)((Kd + 255) / 256), 256, 0, h->stream>>>(h->Y.p, ysum.p, ysum.p + Kd, K, d);
+      CKL();
+    }
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  // Y = arma::normalise(Y, 2, 0)  (harmony.cpp:136)
   k_normalise_rows<<<grid_for((int64_t)h->K * 32, 256, 64), 256, 0, h->stream>>>(h->Y.p, h->Y.p, h->K, h->d, h->d);
   CKL();
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));

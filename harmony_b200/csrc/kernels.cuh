@@ -90,6 +90,60 @@ __global__ void k_normalise_rows(const float* __restrict__ src, float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// native k-means initialisation (stand-in for kmeans_centers, utils.cpp:10-64; outside the timed loop)
+// ------------------------------------------------------------------------------------------------
+// seeds: centroid k <- the (cosine-normalised) cell at position k of a keyed random permutation of the
+// GLOBAL cell indices (distinct by construction); each rank writes the seeds it owns, the rest stay 0.
+__global__ void k_kmeans_seed(const float* __restrict__ Zc, const int* __restrict__ inv_sort, float* __restrict__ Y,
+                              int K, int d, int DS, int64_t N_global, int64_t cell_offset, int64_t n_local,
+                              int half_bits, uint64_t key) {
+  int k = blockIdx.x;
+  if (k >= K) return;
+  int64_t g = (int64_t)hb_permute_inv((uint64_t)k, (uint64_t)N_global, half_bits, key);
+  int64_t l = g - cell_offset;
+  if (l < 0 || l >= n_local) return;
+  const float* z = Zc + (size_t)inv_sort[l] * DS;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) Y[(size_t)k * d + c] = z[c];
+}
+// one Lloyd assignment pass on the cosine-normalised cells: nearest centroid by largest dot product,
+// accumulate per-cluster sums and counts.  Thread per cell, centroids in shared memory.
+__global__ void __launch_bounds__(128) k_kmeans_assign(const float* __restrict__ Zc, const float* __restrict__ Y,
+                                                       float* __restrict__ Ysum, float* __restrict__ cnt,
+                                                       int64_t n, int K, int d, int DS) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ys = smem;  // [K][d]
+  for (int i = threadIdx.x; i < K * d; i += blockDim.x) Ys[i] = Y[i];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* z = Zc + (size_t)i * DS;
+    int best = 0;
+    float bv = -3.0e38f;
+    for (int k = 0; k < K; ++k) {
+      float acc = 0.f;
+      const float* y = Ys + (size_t)k * d;
+      for (int c = 0; c < d; ++c) acc = fmaf(z[c], y[c], acc);
+      // squared Euclidean distance to the (un-normalised) centroid: |z|^2 - 2 z.y + |y|^2 with |z| = 1
+      float yy = 0.f;
+      for (int c = 0; c < d; ++c) yy = fmaf(y[c], y[c], yy);
+      float score = 2.f * acc - yy;
+      if (score > bv) {
+        bv = score;
+        best = k;
+      }
+    }
+    atomicAdd(cnt + best, 1.f);
+    for (int c = 0; c < d; ++c) atomicAdd(Ysum + (size_t)best * d + c, z[c]);
+  }
+}
+__global__ void k_kmeans_update(float* __restrict__ Y, const float* __restrict__ Ysum, const float* __restrict__ cnt,
+                                int K, int d) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * d) return;
+  float c = cnt[idx / d];
+  if (c > 0.f) Y[idx] = Ysum[idx] / c;  // empty clusters keep their centroid (arma::kmeans keep_existing)
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: assignment from the centroids — harmony.cpp:141-150 (init) and :220-227 (cold start)
 //   Zc <- L2-normalised rows (cold start only), dist = 2(1 - Y^T z), U = -dist/sigma,
 //   R = exp(U)/sum_k exp(U), O[b] += column sums of R per level, rs += row sums (for E),

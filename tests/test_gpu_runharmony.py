@@ -1,0 +1,136 @@
+"""End-to-end tests through RunHarmony() with the native (seeded) k-means initialisation and update
+orders — the reference's own testthat files, test for test
+(/root/reference/tests/testthat/test_integration.R, test_two_variable.R), plus determinism and
+size-independent properties at BASELINE.json's 1M-cell configuration."""
+import numpy as np
+import pytest
+
+from harmony_b200 import RunHarmony, harmony_options
+from helpers import load_cell_lines, load_pbmc, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def obj_small():
+    Z, meta = load_cell_lines(True)
+    # test_integration.R:5-7
+    return RunHarmony(Z, meta, "dataset", theta=1, nclust=50, max_iter=5, return_object=True, verbose=False,
+                      options=harmony_options(max_iter_cluster=10), seed=1)
+
+
+def test_dimensions_match(obj_small):
+    obj = obj_small  # test_integration.R:9-14
+    assert obj.Y.shape == (obj.d, obj.K)
+    assert obj.getZcorr().shape == (obj.d, obj.N)
+    assert obj.getZorig().shape == (obj.d, obj.N)
+    assert obj.R.shape == (obj.K, obj.N)
+
+
+def test_R_is_a_probability_distribution(obj_small):
+    R = obj_small.R  # test_integration.R:16-20
+    assert R.min() >= 0 and R.max() <= 1
+    np.testing.assert_allclose(R.sum(axis=0), 1.0, atol=1e-5)
+
+
+def test_no_null_values(obj_small):
+    Z = obj_small.getZcorr()  # test_integration.R:22-26
+    assert np.all(np.isfinite(Z))
+
+
+def _chi2(o):
+    return float((((o.O - o.E) ** 2) / o.E).sum())
+
+
+def test_theta_decreases_chi2():
+    Z, meta = load_cell_lines(True)  # test_integration.R:29-41
+    o0 = RunHarmony(Z, meta, "dataset", theta=0, nclust=20, max_iter=2, return_object=True, verbose=False, seed=2)
+    o1 = RunHarmony(Z, meta, "dataset", theta=1, nclust=5, max_iter=2, return_object=True, verbose=False, seed=2)
+    assert _chi2(o0) > _chi2(o1)
+
+
+def test_error_messages():
+    Z, meta = load_cell_lines(True)  # test_integration.R:43-55
+    with pytest.raises(ValueError):
+        RunHarmony(Z, meta, "fake_variable", verbose=False)
+    with pytest.raises(ValueError):
+        RunHarmony(Z, meta, "dataset", lambda_=[1, 2], verbose=False)
+    with pytest.raises(ValueError):
+        RunHarmony(Z, {k: v[:-1] for k, v in meta.items()}, "dataset", verbose=False)
+    with pytest.raises(TypeError):
+        RunHarmony(Z, meta, "dataset", tau=1, verbose=False)   # legacy argument
+
+
+def test_two_variable_run():
+    Z, meta = load_cell_lines(False)  # test_two_variable.R:5-55
+    obj = RunHarmony(Z, meta, ["cell_type", "dataset"], theta=[1, 1], nclust=50, max_iter=10, return_object=True,
+                     verbose=False, options=harmony_options(max_iter_cluster=10), seed=3)
+    assert obj.Y.shape == (obj.d, obj.K) and obj.R.shape == (obj.K, obj.N)
+    assert obj.O.shape[1] == 5 and obj.E.shape[1] == 5
+    R = obj.R
+    assert R.min() >= 0 and R.max() <= 1
+    np.testing.assert_allclose(R.sum(axis=0), 1.0, atol=1e-5)
+    assert np.all(np.isfinite(obj.getZcorr()))
+    lo = RunHarmony(Z, meta, ["cell_type", "dataset"], theta=[0, 0], nclust=20, max_iter=2, return_object=True,
+                    verbose=False, seed=4)
+    hi = RunHarmony(Z, meta, ["cell_type", "dataset"], theta=[2, 2], nclust=20, max_iter=2, return_object=True,
+                    verbose=False, seed=4)
+    assert _chi2(lo) > _chi2(hi)
+
+
+def test_returns_embedding_and_mixes_batches():
+    """Default call returns cells x PCs; on pbmc_stim (config 2) the stim/ctrl batches mix: the mean
+    per-cluster batch imbalance drops markedly."""
+    Z, meta = load_pbmc()
+    out = RunHarmony(Z, meta, "stim", nclust=50, verbose=False, seed=5)
+    assert out.shape == Z.shape and np.all(np.isfinite(out))
+    obj = RunHarmony(Z, meta, "stim", nclust=50, verbose=False, seed=5, return_object=True)
+    first = RunHarmony(Z, meta, "stim", nclust=50, verbose=False, seed=5, return_object=True, max_iter=0)
+    assert _chi2(obj) < _chi2(first)
+    assert len(obj.objective_harmony) == len(obj.kmeans_rounds) + 1
+
+
+def test_seed_reproducible_and_seed_dependent():
+    Z, meta = synthetic(5000, 20, [4], seed=9)
+    a = RunHarmony(Z, meta, "cov0", nclust=20, max_iter=3, verbose=False, seed=11)
+    b = RunHarmony(Z, meta, "cov0", nclust=20, max_iter=3, verbose=False, seed=11)
+    c = RunHarmony(Z, meta, "cov0", nclust=20, max_iter=3, verbose=False, seed=12)
+    assert np.linalg.norm(a - b) / np.linalg.norm(a) < 1e-5      # same seed: same orders (atomics reorder sums)
+    assert np.linalg.norm(a - c) / np.linalg.norm(a) > 1e-6      # another seed: another run
+
+
+def test_properties_at_full_size():
+    """BASELINE.json config 3 (1M cells x 50 PCs, 20 batches, K=100): size-independent invariants."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synth_shard
+    from harmony_b200.harmony import harmony
+    N = 1_000_000
+    Z, b = synth_shard(N, 0, 123)
+    g = harmony()
+    g.setup(Z, b.reshape(-1, 1), np.full(100, 0.1), np.full(20, 2.0), None, 0.2, 4, 1e-3, -np.inf, 100, 0.05,
+            np.array([20], dtype=np.int32), 1e-5)
+    g.set_seed(7)
+    g.init_cluster_cpp()
+    N_b = np.bincount(b, minlength=20)
+    for it in range(2):
+        assert g.cluster_cpp() == 0
+        O, E = g.O, g.E
+        # O column sums = batch sizes, E column sums = batch sizes, rows of O and E agree (sum_b O_kb = sum_i R_ik)
+        np.testing.assert_allclose(O.sum(axis=0), N_b, rtol=2e-4)
+        np.testing.assert_allclose(E.sum(axis=0), N_b, rtol=2e-4)
+        np.testing.assert_allclose(O.sum(axis=1), E.sum(axis=1), rtol=2e-4)
+        g.moe_correct_ridge_cpp()
+        g.check_convergence(1)
+    R = g.R
+    np.testing.assert_allclose(R.sum(axis=0), 1.0, atol=2e-5)
+    assert R.min() >= 0
+    np.testing.assert_allclose(R.sum(axis=1), g.O.sum(axis=1), rtol=2e-4)   # O is consistent with the stored R
+    Zc = g.getZcorr()
+    assert np.all(np.isfinite(Zc))
+    np.testing.assert_allclose(np.linalg.norm(g.Y, axis=0), 1.0, atol=1e-5)  # centroids are unit vectors
+    ok = g.objective_kmeans
+    assert len(ok) == 1 + 2 * 4 and np.all(np.isfinite(ok))
+    # idempotence of the read path and un-sorting: getZorig returns the input (fp32-rounded), in input order
+    np.testing.assert_array_equal(g.getZorig().T[:1000], Z[:1000].astype(np.float32))
