@@ -20,6 +20,25 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
+// Single-instruction transcendental approximations (MUFU, flush-to-zero): the intrinsics __expf / __logf /
+// __frcp_rn expand to range-handling sequences (extra FSETP / FMUL / branches) that the issue-bound row
+// loops cannot afford.  Relative error ~2^-22.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_log(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.6931471805599453f;
+}
+
 // Streaming (read-once) global loads: keep them out of L1 so the small tables stay resident.
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "update_kernel.cuh"
 #include "assign_tc.cuh"
+#include "apply_tc.cuh"
 
 namespace {
 
@@ -137,9 +138,11 @@ struct hb_handle {
   DevBuf<int> sort_perm, inv_sort, tuple_levels, cov_of_d, tile_cell0, tile_len, tile_tuple, chunk_start,
       tuple_chunk0, blk_of, order, prev_at, H, seg_start, tile_base, iscratch, skipped, err_flag;
   DevBuf<int64_t> perms_d;
+  DevBuf<int4> ranges;  // [T][nb][coop_grid] tuple-aligned CTA ranges (when 2 J <= grid)
+  bool aligned_ranges = false;
   DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
   int tc_ntiles = 0;
-  bool use_tc_assign = false;
+  bool use_tc_assign = false, use_tc_apply = false;
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
@@ -471,6 +474,11 @@ int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, o
   k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
                                                                     seg_start, tile_base);
   CKL();
+  if (h->use_v2 && h->aligned_ranges) {
+    k_plan_ranges<<<(nb + 63) / 64, 64, 0, h->stream>>>(seg_start, nb, J, h->coop_grid,
+                                                        h->ranges.p + (size_t)t * nb * h->coop_grid);
+    CKL();
+  }
   if (!h->use_v2) {
     k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(seg_start, S, tile_base);
     CKL();
@@ -572,6 +580,7 @@ UpdArgs make_upd_args(hb_handle* h, int T) {
   a.order = h->order.p;
   a.seg_start = h->seg_start.p;
   a.prev_at = h->prev_at.p;
+  a.ranges = h->aligned_ranges ? h->ranges.p : nullptr;
   a.tuple_levels = h->tuple_levels.p;
   a.sigma = h->sigma.p;
   a.theta = h->theta.p;
@@ -750,6 +759,51 @@ int run_correct(hb_handle* h) {
     a.cutoff = h->cutoff;
     k_ridge_solve<<<K, 256, sizeof(int) * (size_t)(B + C), h->stream>>>(a);
     CKL();
+  }
+  if (h->use_tc_apply) {
+    RegionScope rs(h, "ridge_apply");
+    ApplyTcArgs a;
+    a.R = h->R.p;
+    a.Zo = h->Zo.p;
+    a.V = h->V.p;
+    a.Zc = h->Zc.p;
+    a.tile_cell0 = h->tile_cell0.p;
+    a.tile_len = h->tile_len.p;
+    a.tile_tuple = h->tile_tuple.p;
+    a.ntiles = h->ntiles;
+    a.d = d;
+    a.K = K;
+    a.KS = h->KS;
+    a.DS = h->DS;
+    a.KD = (K + 7) & ~7;
+    a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
+    a.dbg = nullptr;
+    static int ap_calls = 0;
+    const bool tracing = getenv("HB_TRACE_APPLY") != nullptr && (++ap_calls == 4);
+    if (tracing) {
+      if (h->dbg.n < 64 * 12) CK(h->dbg.alloc(64 * 12));
+      CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 64 * 12, h->stream));
+      a.dbg = h->dbg.p;
+    }
+    const size_t smem = apply_tc_smem_bytes(a.KD);
+    CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
+    CKL();
+    if (tracing) {
+      std::vector<long long> st(64 * 12);
+      CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (FILE* f = fopen("gpurun_out/apply_trace.txt", "w")) {
+        for (int i = 0; i < 64; ++i) {
+          fprintf(f, "%d", i);
+          for (int k = 0; k < 12; ++k) fprintf(f, " %lld", st[(size_t)i * 12 + k]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
+    return 0;
   }
   {
     RegionScope rs(h, "ridge_apply");
@@ -1180,6 +1234,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tc_cell0.alloc(h->tc_ntiles));
   CK(h->tc_len.alloc(h->tc_ntiles));
   CK(h->tc_tuple.alloc(h->tc_ntiles));
+  h->use_tc_apply = (K <= 128) && (d <= 64) && apply_tc_smem_bytes((K + 7) & ~7) <= 227 * 1024 &&
+                    (getenv("HB_APPLY_TC") != nullptr);  // opt-in: the FFMA kernel is still faster (loader-bound TC version)
   h->use_tc_assign = (h->DS <= 4 * TC_DS4MAX) && (KS <= 256) &&
                      assign_tc_smem_bytes((d + 7) & ~7, (K + 15) & ~15, KS) <= 227 * 1024 && (getenv("HB_ASSIGN_FFMA") == nullptr);
   CK(h->chunk_start.alloc(h->nchunks + 1));
@@ -1197,6 +1253,9 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->OEend.alloc((size_t)Tplan * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)Tplan));
     CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));
+    h->coop_grid = h->num_sms;  // one persistent CTA per SM
+    h->aligned_ranges = (2 * J <= h->coop_grid);
+    if (h->aligned_ranges) CK(h->ranges.alloc((size_t)Tplan * h->nb * h->coop_grid));
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
       CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));
@@ -1322,6 +1381,7 @@ int ensure_plan_rounds(hb_handle* h, int T) {
     CK(h->OEend.alloc((size_t)T * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)T));
     CK(h->bar.alloc(2 * ((size_t)T * h->nb + 2)));
+    if (h->aligned_ranges) CK(h->ranges.alloc((size_t)T * h->nb * h->coop_grid));
   }
   h->plan_rounds = T;
   return 0;

@@ -75,6 +75,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
+// Same, 128-byte swizzled layouts (layout_type = SWIZZLE_128B); the tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
+}
 // Instruction descriptor of tcgen05.mma.kind::tf32, fp32 accumulate, dense.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                      // c_format  = F32

@@ -32,8 +32,8 @@ constexpr int UPD_RPW = 32 / UPD_LPR;        // rows per warp
 constexpr int UPD_BATCH = UPD_GWARPS * UPD_RPW;  // rows per batch per group
 constexpr int UPD_STAGE = 2048;              // staged order entries per group
 // cp.async stages per warp: the look-ahead group streams from HBM (deep), the update group re-reads from L2
-__host__ __device__ constexpr int upd_depth_look(int nv) { return nv <= 2 ? 8 : 3; }
-__host__ __device__ constexpr int upd_depth_upd(int nv) { return nv <= 2 ? 3 : 2; }
+__host__ __device__ constexpr int upd_depth_look(int nv) { return nv <= 2 ? 8 : 2; }
+__host__ __device__ constexpr int upd_depth_upd(int nv) { return nv <= 2 ? 4 : 2; }
 constexpr int UPD_RUNAHEAD = 3;              // block steps the look-ahead group may run ahead of the update group
 
 struct UpdArgs {
@@ -42,6 +42,7 @@ struct UpdArgs {
   const int* order;      // [T][n]   rows sorted by (block, tuple, cell) per round
   const int* prev_at;    // [T][n]   block (in the previous round) of the cell at each position of `order`
   const int* seg_start;  // [T][nb*J + 1]
+  const int4* ranges;    // [T*nb][grid] (lo, hi, tuple, 0): tuple-aligned CTA ranges, or null (even split)
   const int* tuple_levels;  // [J][C]
   const float* sigma;    // [K]
   const float* theta;    // [B]
@@ -206,21 +207,33 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
   };
 
   // ---- one block (round t, block j = step s) processed by the calling warp group ------------------
-  auto process = [&](int s, auto mode_c) {
+  // pre_wait: blocks until the step's inputs (counters) are complete; called after the plan data of the
+  // step has been staged and the first row loads are in flight, right before the tables are derived
+  auto process = [&](int s, auto mode_c, auto&& pre_wait) {
     constexpr int mode = decltype(mode_c)::value;
     constexpr int DEPTH = (mode == MODE_UPDATE) ? DEPTH_U : DEPTH_L;
     const int t = s / nb, j = s - t * nb;
-    {
+    const bool single = a.ranges != nullptr;  // this CTA's rows of the block belong to ONE tuple
+    int lo, hi, q = 0;
+    if (single) {
+      const int4 rg = __ldg(a.ranges + (size_t)s * gridDim.x + blockIdx.x);
+      lo = rg.x;
+      hi = rg.y;
+      q = rg.z;
+    } else {
       const int* ss = a.seg_start + (size_t)t * (nb * J + 1) + (size_t)j * J;
       for (int i = gt; i <= J; i += UPD_GROUP) segs[i] = ss[i];
+      group_sync(bar_id);
+      const int b0 = segs[0], b1 = segs[J];
+      const int64_t blen = b1 - b0;
+      lo = b0 + (int)((blen * blockIdx.x) / gridDim.x);
+      hi = b0 + (int)((blen * (blockIdx.x + 1)) / gridDim.x);
     }
-    group_sync(bar_id);
     stamp(s - (mode == MODE_UPDATE ? 0 : 1), 1);
-    const int b0 = segs[0], b1 = segs[J];
-    const int64_t blen = b1 - b0;
-    const int lo = b0 + (int)((blen * blockIdx.x) / gridDim.x);
-    const int hi = b0 + (int)((blen * (blockIdx.x + 1)) / gridDim.x);
-    if (lo >= hi) return;
+    if (lo >= hi) {
+      pre_wait();
+      return;
+    }
     const int* order = a.order + (size_t)t * a.n;
     const int* prev_at = a.prev_at + (size_t)t * a.n;
     const bool writeR = (mode == MODE_UPDATE) && ((a.write_R_mask >> t) & 1u);
@@ -241,8 +254,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) cs[v][c] = 0.f;
 
-    int q = 0;
-    {  // last q with segs[q] <= lo
+    if (!single) {  // last q with segs[q] <= lo
       int l = 0, h = J;
       while (h - l > 1) {
         int m = (l + h) >> 1;
@@ -250,6 +262,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
       }
       q = l;
     }
+    bool waited = false;
     for (int c0 = lo; c0 < hi; c0 += UPD_STAGE) {  // staged chunks of the CTA's range
       const int c1 = min(hi, c0 + UPD_STAGE);
       group_sync(bar_id);
@@ -261,8 +274,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
       stamp(s - (mode == MODE_UPDATE ? 0 : 1), 2);
       int p = c0;
       while (p < c1) {
-        while (segs[q + 1] <= p) ++q;  // skip empty segments
-        const int run_end = min(c1, segs[q + 1]);
+        if (!single)
+          while (segs[q + 1] <= p) ++q;  // skip empty segments
+        const int run_end = single ? c1 : min(c1, segs[q + 1]);
         // --- start the cp.async row pipeline (DEPTH-1 batches), then derive this run's tables behind it
         const float* src = (mode == MODE_LOOK_R) ? a.R : a.U;
         auto issue = [&](int r0, int stage) {
@@ -283,6 +297,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
         int r0 = p + gw * UPD_RPW;
 #pragma unroll
         for (int i = 0; i < DEPTH - 1; ++i) issue(r0 + i * UPD_BATCH, i);
+        if (!waited) {
+          pre_wait();
+          waited = true;
+        }
         if constexpr (mode == MODE_UPDATE) {
           TableView tv = tables_for(s);
           for (int k = gt; k < KS; k += UPD_GROUP) {
@@ -327,22 +345,39 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
         }
         group_sync(bar_id);
         stamp(s - (mode == MODE_UPDATE ? 0 : 1), 3);
-        // --- pipelined row loop: batch i+1 is loaded while batch i is reduced
+        // --- pipelined row loop: batches i+1 .. i+DEPTH-1 are in flight while batch i is reduced.
+        // The loop is issue-bound: no branches (padding lanes / rows carry U_PAD -> exp = 0), the update
+        // group's loop-invariant table rows live in registers.
+        float4 pP[NV], pL[NV];
+        bool slot_ok[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int q4 = gl + UPD_LPR * v;
+          slot_ok[v] = q4 < KS4;
+          pP[v] = pL[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (mode == MODE_UPDATE) {
+            if (slot_ok[v]) {
+              pP[v] = *reinterpret_cast<const float4*>(tab + q4 * 4);
+              pL[v] = *reinterpret_cast<const float4*>(tab + KS + q4 * 4);
+            }
+          }
+        }
+        const bool sig_u = a.sigma_uniform != 0;
         for (int it = 0; r0 < run_end; r0 += UPD_BATCH, ++it) {
           issue(r0 + (DEPTH - 1) * UPD_BATCH, (it + DEPTH - 1) % DEPTH);
           asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
           __syncwarp();
           const int row = r0 + grp;
           const bool valid = row < run_end;
-          const int jp_b = (valid && mode == MODE_LOOK_U) ? prvS[row - c0] : 0;
+          const int ridx = valid ? row - c0 : 0;
+          const float* bp = rowbuf + ((size_t)(it % DEPTH) * UPD_RPW + grp) * KS;
           float4 ub[NV];
-          {
-            const float* bp = rowbuf + ((size_t)(it % DEPTH) * UPD_RPW + grp) * KS;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int q4 = gl + UPD_LPR * v;
-              ub[v] = (valid && q4 < KS4) ? *reinterpret_cast<const float4*>(bp + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+          for (int v = 0; v < NV; ++v) {
+            const int q4 = gl + UPD_LPR * v;
+            const float pad = (mode == MODE_LOOK_R) ? 0.f : U_PAD;
+            ub[v] = make_float4(pad, pad, pad, pad);
+            if (valid && slot_ok[v]) ub[v] = *reinterpret_cast<const float4*>(bp + q4 * 4);
           }
           if constexpr (mode == MODE_LOOK_R) {
 #pragma unroll
@@ -353,38 +388,37 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
               cs[v][3] += ub[v].w;
             }
           } else {
-            // exp through ex2.approx (2 ulp) and one reciprocal per row: this loop is issue-bound, the
-            // IEEE expf / divisions of the first version cost 3x the instructions (profiles/r01_*)
-            const float* pw = (mode == MODE_UPDATE) ? tab : tab + (size_t)jp_b * KS;
+            // exp through ex2.approx (2 ulp) and one reciprocal per row (IEEE expf / divides cost 3x)
             float ssum = 0.f, Aacc = 0.f, Bacc = 0.f, Sacc = 0.f;
+            const float* pw = tab + (size_t)((mode == MODE_LOOK_U) ? prvS[ridx] : 0) * KS;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {  // ub[v] <- exp(u) * Psum (the un-normalised R, >= 0)
               const int q4 = gl + UPD_LPR * v;
-              if (valid && q4 < KS4) {
-                const float4 p4 = *reinterpret_cast<const float4*>(pw + q4 * 4);
-                const float4 u4 = ub[v];
-                ub[v].x = __expf(u4.x) * p4.x;
-                ub[v].y = __expf(u4.y) * p4.y;
-                ub[v].z = __expf(u4.z) * p4.z;
-                ub[v].w = __expf(u4.w) * p4.w;
-                if constexpr (mode == MODE_UPDATE) {
-                  const float4 l4 = *reinterpret_cast<const float4*>(tab + KS + q4 * 4);
-                  if (a.sigma_uniform) {
-                    Aacc = fmaf(ub[v].x, u4.x, Aacc); Bacc = fmaf(ub[v].x, l4.x, Bacc);
-                    Aacc = fmaf(ub[v].y, u4.y, Aacc); Bacc = fmaf(ub[v].y, l4.y, Bacc);
-                    Aacc = fmaf(ub[v].z, u4.z, Aacc); Bacc = fmaf(ub[v].z, l4.z, Bacc);
-                    Aacc = fmaf(ub[v].w, u4.w, Aacc); Bacc = fmaf(ub[v].w, l4.w, Bacc);
-                  } else {
-                    const float4 s4 = *reinterpret_cast<const float4*>(sig + q4 * 4);
-                    float tt;
-                    tt = s4.x * ub[v].x; Aacc = fmaf(tt, u4.x, Aacc); Bacc = fmaf(tt, l4.x, Bacc); Sacc += tt;
-                    tt = s4.y * ub[v].y; Aacc = fmaf(tt, u4.y, Aacc); Bacc = fmaf(tt, l4.y, Bacc); Sacc += tt;
-                    tt = s4.z * ub[v].z; Aacc = fmaf(tt, u4.z, Aacc); Bacc = fmaf(tt, l4.z, Bacc); Sacc += tt;
-                    tt = s4.w * ub[v].w; Aacc = fmaf(tt, u4.w, Aacc); Bacc = fmaf(tt, l4.w, Bacc); Sacc += tt;
-                  }
+              float4 p4 = pP[v];
+              if constexpr (mode == MODE_LOOK_U) {
+                p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (slot_ok[v]) p4 = *reinterpret_cast<const float4*>(pw + q4 * 4);
+              }
+              const float4 u4 = ub[v];
+              ub[v].x = fast_exp(u4.x) * p4.x;
+              ub[v].y = fast_exp(u4.y) * p4.y;
+              ub[v].z = fast_exp(u4.z) * p4.z;
+              ub[v].w = fast_exp(u4.w) * p4.w;
+              if constexpr (mode == MODE_UPDATE) {
+                const float4 l4 = pL[v];
+                if (sig_u) {
+                  Aacc = fmaf(ub[v].x, u4.x, Aacc); Bacc = fmaf(ub[v].x, l4.x, Bacc);
+                  Aacc = fmaf(ub[v].y, u4.y, Aacc); Bacc = fmaf(ub[v].y, l4.y, Bacc);
+                  Aacc = fmaf(ub[v].z, u4.z, Aacc); Bacc = fmaf(ub[v].z, l4.z, Bacc);
+                  Aacc = fmaf(ub[v].w, u4.w, Aacc); Bacc = fmaf(ub[v].w, l4.w, Bacc);
+                } else {
+                  const float4 s4 = slot_ok[v] ? *reinterpret_cast<const float4*>(sig + q4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  float tt;
+                  tt = s4.x * ub[v].x; Aacc = fmaf(tt, u4.x, Aacc); Bacc = fmaf(tt, l4.x, Bacc); Sacc += tt;
+                  tt = s4.y * ub[v].y; Aacc = fmaf(tt, u4.y, Aacc); Bacc = fmaf(tt, l4.y, Bacc); Sacc += tt;
+                  tt = s4.z * ub[v].z; Aacc = fmaf(tt, u4.z, Aacc); Bacc = fmaf(tt, l4.z, Bacc); Sacc += tt;
+                  tt = s4.w * ub[v].w; Aacc = fmaf(tt, u4.w, Aacc); Bacc = fmaf(tt, l4.w, Bacc); Sacc += tt;
                 }
-              } else {
-                ub[v] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
               ssum += (ub[v].x + ub[v].y) + (ub[v].z + ub[v].w);
             }
@@ -393,8 +427,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
             ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
             ssum += __shfl_xor_sync(0xffffffffu, ssum, 8);
             const float sdiv = (ssum == 0.f) ? 1.f : ssum;  // arma::normalise(.., 1, 0): zero norm divides by 1
-            const float inv = 1.f / sdiv;
-            float4* rp = reinterpret_cast<float4*>(a.R + (size_t)(valid ? ordS[row - c0] : 0) * KS);
+            const float inv = fast_rcp(sdiv);
+            float4* rp = reinterpret_cast<float4*>(a.R + (size_t)ordS[ridx] * KS);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
               const int q4 = gl + UPD_LPR * v;
@@ -407,12 +441,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
               cs[v][1] += r.y;
               cs[v][2] += r.z;
               cs[v][3] += r.w;
-              if (writeR && valid && q4 < KS4) rp[q4] = r;
+              if (writeR && valid && slot_ok[v]) rp[q4] = r;
             }
             if constexpr (mode == MODE_UPDATE) {
               // sum_k R dist = -sum sigma R U ;  sum_k sigma R log R = sum sigma R (U + log Psum - log s)
-              const float ls = __logf(sdiv);
-              if (a.sigma_uniform) {
+              const float ls = fast_log(sdiv);
+              if (sig_u) {
                 // per lane: Sacc would be this lane's share of ssum; use the row total once (lane gl == 0)
                 const float srow = (gl == 0) ? ssum : 0.f;
                 okd -= a.sigma0 * inv * Aacc;
@@ -492,22 +526,19 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
     }
     group_sync(bar_id);
   };
-  auto look = [&](int s) {
-    if (s < nb && a.first_round_from_R)
-      process(s, std::integral_constant<int, MODE_LOOK_R>());
-    else
-      process(s, std::integral_constant<int, MODE_LOOK_U>());
-  };
+  auto no_wait = [&]() {};
   if (gid == 0) {
     // ---------------- update group: the critical path ----------------
     for (int s = a.s_begin; s < a.s_end; ++s) {
-      if (a.use_barrier) {
-        if (s > a.s_begin) wait_for(cntU + s - 1);                 // add_{s-1}, ring, Psave of step s-1
-        if (s > a.s_begin || a.prologue) wait_for(cntL + s);       // rem_s
-      }
       stamp(s, 0);
-      owners(s);
-      process(s, std::integral_constant<int, MODE_UPDATE>());
+      auto waits = [&]() {
+        if (a.use_barrier) {
+          if (s > a.s_begin) wait_for(cntU + s - 1);                 // add_{s-1}, ring, Psave of step s-1
+          if (s > a.s_begin || a.prologue) wait_for(cntL + s);       // rem_s
+        }
+        owners(s);
+      };
+      process(s, std::integral_constant<int, MODE_UPDATE>(), waits);
       if ((s + 1) % nb == 0) flush_objective(s / nb);
       stamp(s, 6);
       if (a.use_barrier) signal(cntU + s);
@@ -518,15 +549,20 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
     const int first = a.prologue ? a.s_begin : a.s_begin + 1;
     const int last = (a.s_end < S_total) ? a.s_end : S_total - 1;   // look-ahead targets: first .. last
     for (int s = first; s <= last; ++s) {
-      if (a.use_barrier) {
-        const int t = s / nb;
-        // tables of the previous round must all be saved (its last step's owners signal through cntU)
-        int need = (t > 0) ? t * nb - 1 : -1;
-        const int bound = s - UPD_RUNAHEAD;                           // L2 footprint: stay <= UPD_RUNAHEAD steps ahead
-        if (bound > need) need = bound;
-        if (need >= a.s_begin) wait_for(cntU + need);
-      }
-      look(s);
+      auto waits = [&]() {
+        if (a.use_barrier) {
+          const int t = s / nb;
+          // tables of the previous round must all be saved (its last step's owners signal through cntU)
+          int need = (t > 0) ? t * nb - 1 : -1;
+          const int bound = s - UPD_RUNAHEAD;                           // L2 footprint: stay <= UPD_RUNAHEAD steps ahead
+          if (bound > need) need = bound;
+          if (need >= a.s_begin) wait_for(cntU + need);
+        }
+      };
+      if (s < nb && a.first_round_from_R)
+        process(s, std::integral_constant<int, MODE_LOOK_R>(), waits);
+      else
+        process(s, std::integral_constant<int, MODE_LOOK_U>(), waits);
       if (a.use_barrier) signal(cntL + s);
     }
   }
