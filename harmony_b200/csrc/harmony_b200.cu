@@ -23,6 +23,7 @@
 #include "update_kernel.cuh"
 #include "assign_tc.cuh"
 #include "apply_tc.cuh"
+#include "stats_tc.cuh"
 
 namespace {
 
@@ -128,7 +129,12 @@ struct hb_handle {
   DevBuf<unsigned> bar;
   DevBuf<long long> dbg;  // optional step-phase timestamps (HB_TRACE_STEPS=<cta>)
   int dbg_cta = -1;
-  int plan_rounds = 0;   // rounds the plan buffers hold
+  int plan_rounds = 0;   // rounds each plan buffer set holds (two sets: current call / prebuilt next call)
+  int plan_set = 0;      // set used by the running cluster_cpp call
+  bool next_ready = false;  // the other set holds a prebuilt native plan for the next call ...
+  int next_T = 0;           // ... covering this many rounds
+  cudaStream_t plan_stream = nullptr;
+  cudaEvent_t plan_done = nullptr;
   bool use_v2 = true;
   bool sigma_uniform = false;
   float sigma0 = 0.f;
@@ -142,7 +148,7 @@ struct hb_handle {
   bool aligned_ranges = false;
   DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
   int tc_ntiles = 0;
-  bool use_tc_assign = false, use_tc_apply = false;
+  bool use_tc_assign = false, use_tc_apply = false, use_tc_stats = false;
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
@@ -440,49 +446,50 @@ int check_convergence_host(hb_handle* h, int type, int* out) {
 }
 
 // ---- update-order plan of round t (buffers hold plan_rounds rounds) ------------------------------
-int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, or null */) {
+int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, or null */, int set, cudaStream_t st) {
   RegionScope rs(h, "plan");
   const int nb = h->nb, J = h->J, nc = h->nchunks;
   const int64_t n = h->n;
   const int S = nb * J;
-  int* blk_of = h->blk_of.p + (size_t)t * n;
-  int* order = h->order.p + (size_t)t * n;
-  int* seg_start = h->seg_start.p + (size_t)t * (S + 1);
-  int* tile_base = h->tile_base.p + (size_t)t * (S + 1);
+  const size_t R0 = (size_t)set * h->plan_rounds;  // first round slot of this buffer set
+  int* blk_of = h->blk_of.p + (R0 + t) * n;
+  int* order = h->order.p + (R0 + t) * n;
+  int* seg_start = h->seg_start.p + (R0 + t) * (S + 1);
+  int* tile_base = h->tile_base.p + (R0 + t) * (S + 1);
   if (perm_d) {
-    CK(cudaMemsetAsync(blk_of, 0xff, sizeof(int) * (size_t)n, h->stream));
-    k_plan_block_injected<<<grid_for(h->N_global, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+    CK(cudaMemsetAsync(blk_of, 0xff, sizeof(int) * (size_t)n, st));
+    k_plan_block_injected<<<grid_for(h->N_global, 256, h->num_sms * 8), 256, 0, st>>>(
         perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, nb, blk_of, h->err_flag.p);
     CKL();
   } else {
     uint64_t key = hb_mix64(h->seed ^ hb_mix64(h->round_counter + 0x1234567ull));
-    k_plan_block_native<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+    k_plan_block_native<<<grid_for(n, 256, h->num_sms * 8), 256, 0, st>>>(
         h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, nb, h->half_bits, key, blk_of);
     CKL();
   }
   h->round_counter++;
   const int wpb = 8;  // warps per block
   size_t sm = sizeof(int) * (size_t)wpb * nb;
-  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(blk_of, h->chunk_start.p, nc, nb, h->H.p);
+  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(blk_of, h->chunk_start.p, nc, nb, h->H.p);
   CKL();
-  k_scan_exclusive<<<1, 1024, 0, h->stream>>>(h->H.p, (int64_t)nb * nc, nullptr);
+  k_scan_exclusive<<<1, 1024, 0, st>>>(h->H.p, (int64_t)nb * nc, nullptr);
   CKL();
-  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, h->stream>>>(
-      blk_of, h->chunk_start.p, nc, nb, h->H.p, order, (t > 0) ? h->blk_of.p + (size_t)(t - 1) * n : nullptr,
-      h->use_v2 ? h->prev_at.p + (size_t)t * n : nullptr);
+  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(
+      blk_of, h->chunk_start.p, nc, nb, h->H.p, order, (t > 0) ? h->blk_of.p + (R0 + t - 1) * n : nullptr,
+      h->use_v2 ? h->prev_at.p + (R0 + t) * n : nullptr);
   CKL();
-  k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
+  k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
                                                                     seg_start, tile_base);
   CKL();
   if (h->use_v2 && h->aligned_ranges) {
-    k_plan_ranges<<<(nb + 63) / 64, 64, 0, h->stream>>>(seg_start, nb, J, h->coop_grid,
-                                                        h->ranges.p + (size_t)t * nb * h->coop_grid);
+    k_plan_ranges<<<(nb + 63) / 64, 64, 0, st>>>(seg_start, nb, J, h->coop_grid,
+                                                        h->ranges.p + (R0 + t) * nb * h->coop_grid);
     CKL();
   }
   if (!h->use_v2) {
-    k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, h->stream>>>(seg_start, S, tile_base);
+    k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(seg_start, S, tile_base);
     CKL();
-    k_scan_exclusive<<<1, 1024, 0, h->stream>>>(tile_base, (int64_t)S + 1, nullptr);
+    k_scan_exclusive<<<1, 1024, 0, st>>>(tile_base, (int64_t)S + 1, nullptr);
     CKL();
   }
   return 0;
@@ -499,7 +506,7 @@ int run_update_R_v1(hb_handle* h, int t) {
   StepArgs a;
   a.U = h->U.p;
   a.R = h->R.p;
-  a.order = h->order.p + (size_t)t * h->n;
+  a.order = h->order.p + (size_t)t * h->n;  // v1 always plans into set 0
   a.seg_start = h->seg_start.p + (size_t)t * (S + 1);
   a.tile_base = h->tile_base.p + (size_t)t * (S + 1);
   a.tuple_levels = h->tuple_levels.p;
@@ -577,10 +584,11 @@ UpdArgs make_upd_args(hb_handle* h, int T) {
   UpdArgs a;
   a.U = h->U.p;
   a.R = h->R.p;
-  a.order = h->order.p;
-  a.seg_start = h->seg_start.p;
-  a.prev_at = h->prev_at.p;
-  a.ranges = h->aligned_ranges ? h->ranges.p : nullptr;
+  const size_t R0 = (size_t)h->plan_set * h->plan_rounds;
+  a.order = h->order.p + R0 * h->n;
+  a.seg_start = h->seg_start.p + R0 * ((size_t)h->nb * h->J + 1);
+  a.prev_at = h->prev_at.p + R0 * h->n;
+  a.ranges = h->aligned_ranges ? h->ranges.p + R0 * h->nb * h->coop_grid : nullptr;
   a.tuple_levels = h->tuple_levels.p;
   a.sigma = h->sigma.p;
   a.theta = h->theta.p;
@@ -708,28 +716,49 @@ int run_correct(hb_handle* h) {
   {
     RegionScope rs(h, "ridge_stats");
     CK(cudaMemsetAsync(h->S.p, 0, sizeof(float) * (size_t)J * K * D1, h->stream));
+    if (h->use_tc_stats) {
+      StatsTcArgs t;
+      t.R = h->R.p;
+      t.Zo = h->Zo.p;
+      t.tile_cell0 = h->tile_cell0.p;
+      t.tile_len = h->tile_len.p;
+      t.tile_tuple = h->tile_tuple.p;
+      t.S = h->S.p;
+      t.ntiles = h->ntiles;
+      t.d = d;
+      t.K = K;
+      t.KS = h->KS;
+      t.DS = h->DS;
+      t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
+      const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
+      CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
+      k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+      CKL();
+    } else {
     StatsArgs a;
-    a.R = h->R.p;
-    a.Zo = h->Zo.p;
-    a.tile_cell0 = h->tile_cell0.p;
-    a.tile_len = h->tile_len.p;
-    a.tile_tuple = h->tile_tuple.p;
-    a.S = h->S.p;
-    a.ntiles = h->ntiles;
-    a.d = d;
-    a.K = K;
-    a.KS = (K <= 128) ? K : 128;
-    a.ldR = h->KS;
-    a.ldZ = h->DS;
-    const int KSP = (a.KS + 7) & ~7, DP = (D1 + 3) & ~3;
-    dim3 block(DP / 4, KSP / 8);
-    if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the statistics kernel", d);
-    a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms * 4 - 1) / (h->num_sms * 4));
-    dim3 grid((h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta, (K + a.KS - 1) / a.KS);
-    size_t smem = sizeof(float) * (size_t)TM * (KSP + DP);
-    CK(cudaFuncSetAttribute(k_ridge_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ridge_stats<<<grid, block, smem, h->stream>>>(a);
-    CKL();
+      a.R = h->R.p;
+      a.Zo = h->Zo.p;
+      a.tile_cell0 = h->tile_cell0.p;
+      a.tile_len = h->tile_len.p;
+      a.tile_tuple = h->tile_tuple.p;
+      a.S = h->S.p;
+      a.ntiles = h->ntiles;
+      a.d = d;
+      a.K = K;
+      a.KS = (K <= 128) ? K : 128;
+      a.ldR = h->KS;
+      a.ldZ = h->DS;
+      const int KSP = (a.KS + 7) & ~7, DP = (D1 + 3) & ~3;
+      dim3 block(DP / 4, KSP / 8);
+      if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the statistics kernel", d);
+      a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms * 4 - 1) / (h->num_sms * 4));
+      dim3 grid((h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta, (K + a.KS - 1) / a.KS);
+      size_t smem = sizeof(float) * (size_t)TM * (KSP + DP);
+      CK(cudaFuncSetAttribute(k_ridge_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_ridge_stats<<<grid, block, smem, h->stream>>>(a);
+      CKL();
+    }
     TRY(allreduce_f(h, h->S.p, (size_t)J * K * D1));
   }
   {
@@ -785,7 +814,7 @@ int run_correct(hb_handle* h) {
       CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 64 * 12, h->stream));
       a.dbg = h->dbg.p;
     }
-    const size_t smem = apply_tc_smem_bytes(a.KD);
+    const size_t smem = apply_tc_smem_bytes(a.KD, h->KS);
     CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
     k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
@@ -934,6 +963,8 @@ int hb_create(hb_handle** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->plan_done, cudaEventDisableTiming);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   *out = h;
@@ -943,7 +974,10 @@ int hb_create(hb_handle** out, int device) {
 void hb_destroy(hb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->plan_stream) cudaStreamSynchronize(h->plan_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->plan_done) cudaEventDestroy(h->plan_done);
+  if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1002,6 +1036,8 @@ int hb_set_shard(hb_handle* h, int64_t N_global, int64_t cell_offset) {
 
 int hb_set_seed(hb_handle* h, uint64_t seed) {
   if (!h) return 1;
+  if (h->plan_stream) cudaStreamSynchronize(h->plan_stream);
+  h->next_ready = false;
   h->seed = seed;
   h->round_counter = 0;
   return 0;
@@ -1234,18 +1270,20 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tc_cell0.alloc(h->tc_ntiles));
   CK(h->tc_len.alloc(h->tc_ntiles));
   CK(h->tc_tuple.alloc(h->tc_ntiles));
-  h->use_tc_apply = (K <= 128) && (d <= 64) && apply_tc_smem_bytes((K + 7) & ~7) <= 227 * 1024 &&
-                    (getenv("HB_APPLY_TC") != nullptr);  // opt-in: the FFMA kernel is still faster (loader-bound TC version)
+  h->use_tc_apply = (d <= 64) && (K <= 256) && apply_tc_smem_bytes((K + 7) & ~7, KS) <= 227 * 1024 &&
+                    (getenv("HB_APPLY_FFMA") == nullptr);
+  h->use_tc_stats = (K <= 128) && (d + 1 <= 64) && stats_tc_smem_bytes(KS, h->DS) <= 227 * 1024 &&
+                    (getenv("HB_STATS_FFMA") == nullptr);
   h->use_tc_assign = (h->DS <= 4 * TC_DS4MAX) && (KS <= 256) &&
                      assign_tc_smem_bytes((d + 7) & ~7, (K + 15) & ~15, KS) <= 227 * 1024 && (getenv("HB_ASSIGN_FFMA") == nullptr);
   CK(h->chunk_start.alloc(h->nchunks + 1));
   CK(h->tuple_chunk0.alloc(J));
-  CK(h->blk_of.alloc((size_t)Tplan * N));
-  CK(h->order.alloc((size_t)Tplan * N));
-  CK(h->prev_at.alloc((size_t)Tplan * N));
+  CK(h->blk_of.alloc(2 * (size_t)Tplan * N));
+  CK(h->order.alloc(2 * (size_t)Tplan * N));
+  CK(h->prev_at.alloc(2 * (size_t)Tplan * N));
   CK(h->H.alloc((size_t)h->nb * h->nchunks));
-  CK(h->seg_start.alloc((size_t)Tplan * ((size_t)h->nb * J + 1)));
-  CK(h->tile_base.alloc((size_t)Tplan * ((size_t)h->nb * J + 1)));
+  CK(h->seg_start.alloc(2 * (size_t)Tplan * ((size_t)h->nb * J + 1)));
+  CK(h->tile_base.alloc(2 * (size_t)Tplan * ((size_t)h->nb * J + 1)));
   if (h->use_v2) {
     CK(h->ring.alloc(4 * BK));
     CK(h->acc2.alloc(2 * (BK + KS) * ((size_t)Tplan * h->nb + 2)));
@@ -1255,7 +1293,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));
     h->coop_grid = h->num_sms;  // one persistent CTA per SM
     h->aligned_ranges = (2 * J <= h->coop_grid);
-    if (h->aligned_ranges) CK(h->ranges.alloc((size_t)Tplan * h->nb * h->coop_grid));
+    if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)Tplan * h->nb * h->coop_grid));
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
       CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));
@@ -1369,19 +1407,23 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
 
 int ensure_plan_rounds(hb_handle* h, int T) {
   if (T <= h->plan_rounds) return 0;
+  if (h->plan_stream) CK(cudaStreamSynchronize(h->plan_stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->next_ready = false;
+  h->plan_set = 0;
   const size_t BK = (size_t)h->B * h->KS;
   const size_t S1 = (size_t)h->nb * h->J + 1;
-  CK(h->blk_of.alloc((size_t)T * h->n));
-  CK(h->order.alloc((size_t)T * h->n));
-  CK(h->prev_at.alloc((size_t)T * h->n));
-  CK(h->seg_start.alloc((size_t)T * S1));
-  CK(h->tile_base.alloc((size_t)T * S1));
+  CK(h->blk_of.alloc(2 * (size_t)T * h->n));
+  CK(h->order.alloc(2 * (size_t)T * h->n));
+  CK(h->prev_at.alloc(2 * (size_t)T * h->n));
+  CK(h->seg_start.alloc(2 * (size_t)T * S1));
+  CK(h->tile_base.alloc(2 * (size_t)T * S1));
   if (h->use_v2) {
     CK(h->acc2.alloc(2 * (BK + h->KS) * ((size_t)T * h->nb + 2)));
     CK(h->OEend.alloc((size_t)T * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)T));
     CK(h->bar.alloc(2 * ((size_t)T * h->nb + 2)));
-    if (h->aligned_ranges) CK(h->ranges.alloc((size_t)T * h->nb * h->coop_grid));
+    if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)T * h->nb * h->coop_grid));
   }
   h->plan_rounds = T;
   return 0;
@@ -1408,8 +1450,22 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
   if (h->use_v2) {
     // all T update orders are drawn up front (they do not depend on the data), then the rounds run in
     // chunks: [0, window_size + 2) in one launch, afterwards one round per launch (convergence checks)
-    for (unsigned t = 0; t < T; ++t)
-      TRY(build_plan(h, (int)t, update_orders ? h->perms_d.p + (size_t)t * (size_t)h->N_global : nullptr));
+    // The native orders of a call depend only on (seed, round counter), so the plan of the NEXT call is
+    // prebuilt on a side stream while this call's correction / the next assignment run (two buffer sets).
+    if (h->next_ready) {
+      CK(cudaStreamWaitEvent(h->stream, h->plan_done, 0));  // also serialises the use of the scan scratch
+      if (!update_orders && h->next_T >= (int)T) {
+        h->plan_set ^= 1;  // adopt the prebuilt plan
+      } else {
+        h->round_counter -= (uint64_t)h->next_T;  // discard it: its rounds were never run
+        for (unsigned t = 0; t < T; ++t)
+          TRY(build_plan(h, (int)t, update_orders ? h->perms_d.p + (size_t)t * (size_t)h->N_global : nullptr, h->plan_set, h->stream));
+      }
+      h->next_ready = false;
+    } else {
+      for (unsigned t = 0; t < T; ++t)
+        TRY(build_plan(h, (int)t, update_orders ? h->perms_d.p + (size_t)t * (size_t)h->N_global : nullptr, h->plan_set, h->stream));
+    }
     if (T > 0) TRY(upd_begin_call(h, (int)T));
     unsigned t0 = 0;
     while (t0 < T) {
@@ -1430,7 +1486,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
   } else {
     for (iter = 0; iter < T; iter++) {
       if (iter > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
-      TRY(build_plan(h, 0, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr));
+      TRY(build_plan(h, 0, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr, 0, h->stream));
       TRY(run_update_R_v1(h, 0));  // :241
       TRY(push_objective(h));      // :248
       if (iter > h->window_size) {  // :250-256
@@ -1442,6 +1498,16 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
         }
       }
     }
+  }
+  if (h->use_v2 && !update_orders && T > 0 && !h->timing && getenv("HB_NO_PLAN_OVERLAP") == nullptr) {
+    // prebuild the next call's plan into the other buffer set on the side stream; it starts once this
+    // call's own (main-stream) plan build and update kernel are done with the shared scan scratch
+    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaStreamWaitEvent(h->plan_stream, h->ev0, 0));
+    for (unsigned t = 0; t < T; ++t) TRY(build_plan(h, (int)t, nullptr, h->plan_set ^ 1, h->plan_stream));
+    CK(cudaEventRecord(h->plan_done, h->plan_stream));
+    h->next_ready = true;
+    h->next_T = (int)T;
   }
   if (T > 0) h->R_user_set = false;
   if (update_orders) TRY(check_err_flag(h));

@@ -115,6 +115,16 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = round_tf32(x - hi);     // the remainder (exact in fp32) at tf32 precision
 }
 
+// mbarrier transaction accounting + 1-D bulk (TMA) copy global -> shared: the copy engine completes `bytes`
+// on the barrier; the issuing thread first arms it with arrive.expect_tx.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // 1-D bulk (TMA) copy shared -> global, completion tracked by the bulk async-group of the issuing thread
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
