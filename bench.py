@@ -156,10 +156,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
     n_sample = 200_000
     steps = max(1, min(args.steps, 3))
-    t_iter, blas = cpu_reference_run(n_sample, steps, cores)
+    # the reference only threads its BLAS call (R/ui.R:123-128); time it with all host threads and with the
+    # reference default ncores = 1 and report the faster of the two (skinny sgemm often loses with threads)
+    t_all, blas = cpu_reference_run(n_sample, steps, ncpu)
+    t_one, _ = cpu_reference_run(n_sample, steps, 1) if ncpu > 1 else (t_all, blas)
+    t_iter, cores = (t_all, ncpu) if t_all <= t_one else (t_one, 1)
     v = n_sample / t_iter
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s/iter", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": t_iter * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -167,7 +171,9 @@ def run_reference(args):
             "config": {"workload": f"synthetic {n_sample} cells x {D} PCs, 1 covariate ({B_LEVELS} batches), K={K}"
                                    " (bounded sample of config 3; the algorithm is O(N))"},
             "cpu_baseline": {"value": v, "unit": "cells/s/iter", "cores": cores, "kind": "port",
-                             "sample": f"{n_sample} cells, {steps} timed iteration(s), BLAS={os.path.basename(blas)}"},
+                             "sample": f"{n_sample} cells, {steps} timed iteration(s), BLAS={os.path.basename(blas)}; "
+                                       f"all {ncpu} threads: {n_sample / t_all:.0f} cells/s/iter, 1 thread: "
+                                       f"{n_sample / t_one:.0f} cells/s/iter (faster one reported)"},
             "e2e": {"value": v, "unit": "cells/s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -267,9 +273,10 @@ def main():
     # ---- per-kernel timing pass (region timers: CUDA events on the library stream, extra syncs) -> roofline
     peaks, peak_kind = measured_peaks()
     g.enable_timing(True)
-    base = {r: g.region_time(r) for r in ("k_block_update", "k_block_colsum", "k_step_prepare", "assign", "plan",
-                                           "ridge_stats", "ridge_solve", "ridge_apply", "update_R")}
-    prof_steps = 2
+    names = ("k_update_steps", "k_update_finalize", "k_block_update", "k_block_colsum", "k_step_prepare", "assign",
+             "plan", "ridge_stats", "ridge_solve", "ridge_apply", "update_R")
+    base = {r: g.region_time(r) for r in names}
+    prof_steps = 3
     for _ in range(prof_steps):
         step(g)
     g.synchronize()
@@ -278,21 +285,32 @@ def main():
         ms1, n1 = g.region_time(r)
         reg[r] = {"ms_per_step": (ms1 - ms0) / prof_steps, "launches_per_step": (n1 - n0) / prof_steps}
     g.enable_timing(False)
-    nb = 20
-    upd = reg["k_block_update"]
+    KS, DS, nb = (K + 3) // 4 * 4, (D + 3) // 4 * 4, 20
+    # algorithmic bytes per cell of each hot kernel, fp32
+    algo = {
+        # all T rounds in one launch: per round the U row + its order / previous-block entries; R stored once
+        "k_update_steps": T * (4 * KS + 8) + 4 * KS,
+        "k_block_update": (8 * KS + 4) / nb,            # v1 fallback: one block per launch
+        "assign": 8 * DS + 8 * KS,                       # Zc in/out, U and R out
+        "ridge_stats": 4 * KS + 4 * DS,                  # R and Zo in
+        "ridge_apply": 4 * KS + 8 * DS,                  # R and Zo in, Zc out
+    }
+    timed = {r: reg[r]["ms_per_step"] for r in ("k_update_steps", "k_block_update", "assign", "ridge_stats",
+                                                 "ridge_apply") if reg[r]["launches_per_step"] > 0}
+    total_ms = sum(reg[r]["ms_per_step"] for r in ("update_R", "assign", "plan", "ridge_stats", "ridge_solve",
+                                                   "ridge_apply"))
+    kernels = {}
+    for r, ms_r in timed.items():
+        t_launch = ms_r / reg[r]["launches_per_step"] * 1e-3
+        ach = algo[r] * n_local / t_launch / 1e9
+        kernels[r] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                      "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": algo[r] * n_local,
+                      "avg_launch_us": t_launch * 1e6, "launches_per_step": reg[r]["launches_per_step"],
+                      "share_of_step": ms_r / max(1e-9, total_ms)}
     roofline = None
-    if upd["launches_per_step"] > 0 and upd["ms_per_step"] > 0:
-        # k_block_update: per cell of the block it reads U (4K B) + its order entry (4 B) and writes R (4K B)
-        cells_per_launch = n_local / nb
-        algo_bytes = cells_per_launch * (8 * K + 4)
-        t_launch = upd["ms_per_step"] / upd["launches_per_step"] * 1e-3
-        ach = algo_bytes / t_launch / 1e9
-        roofline = {"kernel": "k_block_update", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
-                    "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_us": t_launch * 1e6,
-                    "share_of_step": upd["ms_per_step"] / max(1e-9, sum(
-                        reg[r]["ms_per_step"] for r in ("update_R", "assign", "plan", "ridge_stats", "ridge_solve",
-                                                        "ridge_apply")))}
+    if kernels:
+        top = max(kernels, key=lambda r: kernels[r]["share_of_step"])
+        roofline = dict(kernel=top, traffic=None, peak_kind=peak_kind, **kernels[top])
     step_ach = ALGO_BYTES_PER_CELL_ITER * n_local / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: public API with host buffers (pinned), H2D of inputs and D2H of the result in the timed region
@@ -346,6 +364,8 @@ def main():
                            "l2": "state (U,R,Z = 1.2 GB per GPU) is ~10x larger than the 126 MB L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline,
+                "roofline_kernels": {r: {k2: (round(v2, 4) if isinstance(v2, float) else v2) for k2, v2 in kv.items()}
+                                     for r, kv in kernels.items()},
                 "roofline_step": {"bound": "hbm", "achieved": step_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": step_ach / peaks["hbm_gbs"],
                                   "algorithmic_bytes_per_cell_iter": ALGO_BYTES_PER_CELL_ITER},

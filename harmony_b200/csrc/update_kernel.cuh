@@ -91,8 +91,14 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
 }
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(UPD_GROUP) : "memory"); }
 
+// ((2E+1)/(O+E+1))^theta (harmony_pow, utils.cpp:84-90) as ex2(theta * lg2(x)): the tables sit on the critical
+// path of every block step and powf costs ~100 instructions; x > 0 here, theta = 0 gives exactly 1.
 __device__ __forceinline__ float penalty_pow(float o_eff, float e_eff, float th) {
-  return powf(((2.f * e_eff) + 1.f) / (o_eff + e_eff + 1.f), th);
+  const float x = ((2.f * e_eff) + 1.f) / (o_eff + e_eff + 1.f);
+  float l, y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(th * l));
+  return y;
 }
 
 struct TableView {
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
     for (int c0 = lo; c0 < hi; c0 += UPD_STAGE) {  // staged chunks of the CTA's range
       const int c1 = min(hi, c0 + UPD_STAGE);
       group_sync(bar_id);
+      if (single && gt < C) segs[gt] = a.tuple_levels[q * C + gt];  // levels of this CTA's tuple (segs is free)
       for (int i = gt; i < c1 - c0; i += UPD_GROUP) {
         ordS[i] = order[c0 + i];
         if (mode == MODE_LOOK_U) prvS[i] = (t > 0) ? prev_at[c0 + i] : 0;
@@ -308,11 +315,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
             if (k < K)
               for (int c = 0; c < C; ++c) {
                 float o, e, pp;
-                derive(tv, a.Pr_b, a.theta, a.tuple_levels[q * C + c], k, o, e, pp);
+                derive(tv, a.Pr_b, a.theta, single ? segs[c] : a.tuple_levels[q * C + c], k, o, e, pp);
                 v += pp;
               }
             tab[k] = v;                              // Psum
-            tab[KS + k] = (k < K) ? logf(v) : 0.f;   // log Psum
+            tab[KS + k] = (k < K) ? fast_log(v) : 0.f;   // log Psum
           }
         } else if constexpr (mode == MODE_LOOK_U) {
           // previous-round penalty sums of tuple q for every block jp: tab[jp][k]
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) k_update_steps(UpdArgs a) {
                   }
                 } else {
                   const float* Ps = a.Psave + ((size_t)(tp & 1) * nb + jp) * BK;
-                  for (int c = 0; c < C; ++c) v += __ldcg(Ps + (size_t)a.tuple_levels[q * C + c] * KS + k);
+                  for (int c = 0; c < C; ++c) v += __ldcg(Ps + (size_t)(single ? segs[c] : a.tuple_levels[q * C + c]) * KS + k);
                 }
               }
             }
