@@ -204,18 +204,28 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    comm = None
     n_local = args.cells_per_gpu
     N_global = n_local * world
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    comm_made = []
+
+    def new_comm():
+        """First object: a fresh NCCL unique id (usable once); later objects share the process-wide
+        communicator (id = None), as a long-lived service would."""
+        if world == 1:
+            return None
+        if comm_made:
+            return (rank, world, None, N_global, rank * n_local)
+        comm_made.append(1)
         import ctypes
         uid = ctypes.create_string_buffer(128)
         if rank == 0:
             assert _lib.lib().hb_comm_unique_id(uid) == 0
         t = torch.tensor(list(uid.raw), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
-        comm = (rank, world, bytes(t.cpu().tolist()), N_global, rank * n_local)
+        return (rank, world, bytes(t.cpu().tolist()), N_global, rank * n_local)
 
     seed = 20260922 + 3
     Z, b = synth_shard(n_local, rank * n_local, seed)
@@ -227,7 +237,7 @@ def main():
         Y0 = ty.cpu().numpy()
 
     def make_obj():
-        g = harmony(device=local_rank, comm=comm)
+        g = harmony(device=local_rank, comm=new_comm())
         g.setup(Z, kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, kw["B_vec"],
                 kw["cutoff"])
         g.set_seed(1234)
@@ -310,7 +320,10 @@ def main():
     roofline = None
     if kernels:
         top = max(kernels, key=lambda r: kernels[r]["share_of_step"])
-        roofline = dict(kernel=top, traffic=None, peak_kind=peak_kind, **kernels[top])
+        # DRAM bytes of one launch of the dominant kernel from the ncu --set full capture of this exact
+        # workload (profiles/r01_final_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum); null otherwise
+        traffic = 3.357287e9 + 0.395527e9 if (top == "k_update_steps" and n_local == CELLS_PER_GPU) else None
+        roofline = dict(kernel=top, traffic=traffic, peak_kind=peak_kind, **kernels[top])
     step_ach = ALGO_BYTES_PER_CELL_ITER * n_local / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: public API with host buffers (pinned), H2D of inputs and D2H of the result in the timed region
@@ -323,7 +336,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        g2 = harmony(device=local_rank, comm=comm)
+        g2 = harmony(device=local_rank, comm=new_comm())
         g2.setup(Zp, kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, kw["B_vec"],
                  kw["cutoff"])
         g2.set_seed(1234)

@@ -16,6 +16,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -64,6 +65,16 @@ bool load_nccl(std::string* why) {
   if (!g_nccl.ok && why) *why = "libnccl lacks required symbols";
   return g_nccl.ok;
 }
+
+// one NCCL communicator per (device, rank, world) is kept for the life of the process and shared by every
+// handle that asks for it with a NULL id (communicator set-up costs ~1 s; models come and go)
+struct CommKey {
+  int device, rank, world;
+  bool operator<(const CommKey& o) const {
+    return std::tie(device, rank, world) < std::tie(o.device, o.rank, o.world);
+  }
+};
+std::map<CommKey, ncclComm_t> g_comms;
 
 struct Region {
   double ms = 0;
@@ -482,7 +493,7 @@ int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, o
                                                                     seg_start, tile_base);
   CKL();
   if (h->use_v2 && h->aligned_ranges) {
-    k_plan_ranges<<<(nb + 63) / 64, 64, 0, st>>>(seg_start, nb, J, h->coop_grid,
+    k_plan_ranges<<<(nb * h->coop_grid + 127) / 128, 128, 0, st>>>(seg_start, nb, J, h->coop_grid,
                                                         h->ranges.p + (R0 + t) * nb * h->coop_grid);
     CKL();
   }
@@ -978,7 +989,6 @@ void hb_destroy(hb_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->plan_done) cudaEventDestroy(h->plan_done);
   if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
-  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   cudaStream_t s = h->stream;
@@ -1019,9 +1029,17 @@ int hb_comm_init(hb_handle* h, int rank, int world_size, const char id[HB_COMM_I
   std::string why;
   if (!load_nccl(&why)) return fail(h, 11, "%s", why.c_str());
   CK(cudaSetDevice(h->device));
+  const CommKey key{h->device, rank, world_size};
+  if (!id) {  // reuse the process-wide communicator created by an earlier handle
+    auto it = g_comms.find(key);
+    if (it == g_comms.end()) return fail(h, 3, "hb_comm_init(NULL id): no communicator has been created yet for this rank/world");
+    h->comm = it->second;
+    return 0;
+  }
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
   CKN(g_nccl.CommInitRank(&h->comm, world_size, uid, rank));
+  g_comms[key] = h->comm;  // kept until process exit
   return 0;
 }
 
@@ -1135,9 +1153,20 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
       key[i] = kk;
     }
   }
-  std::vector<uint64_t> uniq(key);
-  std::sort(uniq.begin(), uniq.end());
-  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  std::vector<uint64_t> uniq;
+  uint64_t key_space = 1;
+  for (int c = 0; c < C; ++c) key_space *= (uint64_t)B_vec[c];
+  const bool small_space = key_space <= (1ull << 22);  // the usual case: a direct table beats sorting N keys
+  if (small_space) {
+    std::vector<uint8_t> seen((size_t)key_space, 0);
+    for (int64_t i = 0; i < N; ++i) seen[key[i]] = 1;
+    for (uint64_t k2 = 0; k2 < key_space; ++k2)
+      if (seen[k2]) uniq.push_back(k2);
+  } else {
+    uniq = key;
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  }
   if (h->world > 1) {
     // global tuple dictionary = union over ranks; level counts summed over ranks
     long long cnt = (long long)uniq.size(), maxcnt = 0;
@@ -1185,10 +1214,17 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   }
   std::vector<int> tuple_of(N);
   std::vector<int64_t> tstart(J + 1, 0);
-  for (int64_t i = 0; i < N; ++i) {
-    int q = (int)(std::lower_bound(uniq.begin(), uniq.end(), key[i]) - uniq.begin());
-    tuple_of[i] = q;
-    tstart[q + 1]++;
+  {
+    std::vector<int> lut;
+    if (small_space) {
+      lut.assign((size_t)key_space, -1);
+      for (int q = 0; q < J; ++q) lut[uniq[q]] = q;
+    }
+    for (int64_t i = 0; i < N; ++i) {
+      int q = small_space ? lut[key[i]] : (int)(std::lower_bound(uniq.begin(), uniq.end(), key[i]) - uniq.begin());
+      tuple_of[i] = q;
+      tstart[q + 1]++;
+    }
   }
   for (int q = 0; q < J; ++q) tstart[q + 1] += tstart[q];
   h->sort_perm_h.resize(N);

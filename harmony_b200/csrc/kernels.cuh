@@ -469,35 +469,36 @@ __global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restr
 }
 // Tuple-aligned work split of every block for the persistent update kernel (G CTAs): each (block, tuple)
 // segment gets a number of CTAs proportional to its length (>= 1), each CTA a contiguous slice of ONE segment.
-// One thread per block; J is small in this mode (2 J <= G).
+// One thread per (block, CTA); every thread replays the O(J) allocation (J is small in this mode: 2 J <= G).
 __global__ void k_plan_ranges(const int* __restrict__ seg_start, int nb, int J, int G, int4* __restrict__ ranges) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nb) return;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nb * G) return;
+  const int j = idx / G, me_cta = idx - j * G;
   const int* segs = seg_start + (size_t)j * J;
-  int4* out = ranges + (size_t)j * G;
   const int b0 = segs[0];
   const long long blen = segs[J] - b0;
-  for (int c = 0; c < G; ++c) out[c] = make_int4(b0, b0, 0, 0);
-  if (blen <= 0) return;
-  int nonempty = 0;
-  for (int q = 0; q < J; ++q) nonempty += (segs[q + 1] > segs[q]);
-  int start = 0;
-  for (int q = 0; q < J; ++q) {
-    const int L = segs[q + 1] - segs[q];
-    if (L == 0) continue;
-    --nonempty;
-    int end = (int)(((long long)G * (segs[q + 1] - b0)) / blen);
-    if (end < start + 1) end = start + 1;
-    if (end > G - nonempty) end = G - nonempty;
-    if (nonempty == 0) end = G;
-    const int nq = end - start;
-    for (int me = 0; me < nq; ++me) {
-      const int lo = segs[q] + (int)(((long long)L * me) / nq);
-      const int hi = segs[q] + (int)(((long long)L * (me + 1)) / nq);
-      out[start + me] = make_int4(lo, hi, q, 0);
+  int4 out = make_int4(b0, b0, 0, 0);
+  if (blen > 0) {
+    int nonempty = 0;
+    for (int q = 0; q < J; ++q) nonempty += (segs[q + 1] > segs[q]);
+    int start = 0;
+    for (int q = 0; q < J; ++q) {
+      const int L = segs[q + 1] - segs[q];
+      if (L == 0) continue;
+      --nonempty;
+      int end = (int)(((long long)G * (segs[q + 1] - b0)) / blen);
+      if (end < start + 1) end = start + 1;
+      if (end > G - nonempty) end = G - nonempty;
+      if (nonempty == 0) end = G;
+      if (me_cta >= start && me_cta < end) {
+        const int nq = end - start, me = me_cta - start;
+        out = make_int4(segs[q] + (int)(((long long)L * me) / nq), segs[q] + (int)(((long long)L * (me + 1)) / nq), q, 0);
+        break;
+      }
+      start = end;
     }
-    start = end;
   }
+  ranges[idx] = out;
 }
 __global__ void k_plan_tilecount(const int* __restrict__ seg_start, int S, int* __restrict__ tile_base) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x) {

@@ -65,9 +65,10 @@ class harmony:
             warnings.warn(buf.value.decode())
 
     def _init_comm(self, comm):
-        """comm = (rank, world_size, id_bytes, N_global, cell_offset); see harmony_b200.dist."""
+        """comm = (rank, world_size, id_bytes or None, N_global, cell_offset); see harmony_b200.dist.
+        ``id_bytes = None`` shares the process-wide communicator an earlier object created."""
         rank, world, uid, n_global, offset = comm
-        self._check(self._L.hb_comm_init(self._h, int(rank), int(world), bytes(uid)))
+        self._check(self._L.hb_comm_init(self._h, int(rank), int(world), None if uid is None else bytes(uid)))
         self._check(self._L.hb_set_shard(self._h, int(n_global), int(offset)))
 
     def _scalar(self, name):

@@ -49,6 +49,8 @@ int hb_version(void);
  * torch.distributed); every rank then calls hb_comm_init BEFORE hb_setup. */
 int hb_comm_unique_id(char id[HB_COMM_ID_BYTES]);
 int hb_comm_init(hb_handle* h, int rank, int world_size, const char id[HB_COMM_ID_BYTES]);
+/* The communicator stays alive for the life of the process; a later handle of the same (device, rank,
+ * world_size) may pass id == NULL to share it instead of paying the ~1 s NCCL set-up again. */
 /* Declares that this handle holds cells [cell_offset, cell_offset + n_local) of an N_global-cell
  * problem.  Must precede hb_setup; without it the handle owns all cells. */
 int hb_set_shard(hb_handle* h, int64_t N_global, int64_t cell_offset);
