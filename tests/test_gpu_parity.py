@@ -203,3 +203,24 @@ def test_field_writes_and_resume():
     g.moe_correct_ridge_cpp()
     g.cluster_cpp(make_perms(300, 10, 1))
     assert len(g.objective_harmony) == 3
+
+
+@pytest.mark.parametrize("env", [
+    {"HB_ASSIGN_FFMA": "1", "HB_STATS_FFMA": "1", "HB_APPLY_FFMA": "1"},   # fp32 FFMA kernels instead of tcgen05
+    {"HB_UPDATE_V1": "1"},                                                 # three launches per block step
+    {"HB_NO_PLAN_OVERLAP": "1"},
+])
+def test_fallback_kernels_match_oracle(env, monkeypatch):
+    """The FFMA / per-step kernels that serve shapes outside the tensor-core kernels' limits
+    (d > 64, K > 128, > 8192 tuples) are the in-repo correctness anchors: same parity bar."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    (Z, meta), vars_use, kw = CASES["synthetic_3cov_nested"]()
+    a = prepare_inputs(Z, meta, vars_use, early_stop=False, **kw)
+    N, T = Z.shape[0], a["max_iter_kmeans"]
+    Y0 = make_Y0(Z, a["K"], 17)
+    perms = make_perms(N, 2 * T, 23).reshape(2, T, N)
+    o32, _, _ = run_oracle(a, Y0, 2, perms=perms)
+    o64, _, _ = run_oracle(a, Y0, 2, perms=perms, double=True)
+    g, iters = run_gpu(a, Y0, 2, perms)
+    compare(g, o32, o64, "fallback " + "+".join(env))
