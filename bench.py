@@ -84,11 +84,36 @@ def setup_kwargs(b, n_levels=B_LEVELS):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML is polled every
+    few milliseconds (the timed region lasts tens of ms); nvidia-smi is the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((sm, self.max_sm, mask))
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -96,10 +121,19 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         while not self._halt.is_set():
             try:
+                if self.nvml is not None:
+                    self._poll_nvml()
+                    self._halt.wait(0.003)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+                    r = [x.strip() for x in out.stdout.strip().split(",")]
+                    mask = 0
+                    for bit, col in ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)):
+                        if len(r) > col and r[col].lower().startswith("active"):
+                            mask |= bit
+                    self.rows.append((float(r[0]), float(r[1]), mask))
             except Exception:
                 pass
             self._halt.wait(0.2)
@@ -107,15 +141,14 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        reasons = []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for i, nm in enumerate(names):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(nm)
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        reasons = [nm for bit, nm in self.REASONS.items() if mask & bit]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():

@@ -90,5 +90,7 @@ def lib():
     L.hb_synchronize.argtypes = [P]
     L.hb_region_time.argtypes = [P, ctypes.c_char_p, ctypes.POINTER(D), ctypes.POINTER(I64)]
     L.hb_enable_timing.argtypes = [P, I]
+    L.hb_debug_permute.restype = ctypes.c_uint64
+    L.hb_debug_permute.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, I]
     _LIB = L
     return L

@@ -14,11 +14,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ int warp_sum_i(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // Single-instruction transcendental approximations (MUFU, flush-to-zero): the intrinsics __expf / __logf /
 // __frcp_rn expand to range-handling sequences (extra FSETP / FMUL / branches) that the issue-bound row

@@ -180,7 +180,7 @@ struct hb_handle {
   int64_t launches = 0;
   bool timing = false;
   std::map<std::string, Region> regions;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr;  // orders the side-stream plan build after the main stream
 };
 
 namespace {
@@ -976,8 +976,7 @@ int hb_create(hb_handle** out, int device) {
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->plan_done, cudaEventDisableTiming);
-  cudaEventCreate(&h->ev0);
-  cudaEventCreate(&h->ev1);
+  cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming);
   *out = h;
   return 0;
 }
@@ -990,7 +989,6 @@ void hb_destroy(hb_handle* h) {
   if (h->plan_done) cudaEventDestroy(h->plan_done);
   if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
   cudaStream_t s = h->stream;
   delete h;  // frees device buffers
   if (s) cudaStreamDestroy(s);
@@ -1752,6 +1750,16 @@ int hb_region_time(hb_handle* h, const char* region, double* ms, int64_t* launch
   if (ms) *ms = it->second.ms;
   if (launches) *launches = it->second.launches;
   return 0;
+}
+
+// Host evaluation of the keyed cell-order permutation used for the native update orders (test hook; the
+// same __host__ __device__ code runs in k_plan_block_native / k_kmeans_seed).
+uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse) {
+  if (n == 0 || i >= n) return ~0ull;
+  int bits = 1;
+  while ((1ull << bits) < n) bits++;
+  const int half_bits = (bits + 1) / 2;
+  return inverse ? hb_permute_inv(i, n, half_bits, key) : hb_permute(i, n, half_bits, key);
 }
 
 int hb_enable_timing(hb_handle* h, int on) {

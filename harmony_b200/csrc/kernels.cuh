@@ -44,14 +44,6 @@ __global__ void k_download_rows(const float* __restrict__ src, double* __restric
     out[idx] = (double)src[(int64_t)src_row[r0 + r] * ld + c];
   }
 }
-__global__ void k_f2d(const float* __restrict__ src, double* __restrict__ out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = (double)src[i];
-}
-__global__ void k_d2f(const double* __restrict__ src, float* __restrict__ out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = (float)src[i];
-}
 __global__ void k_fill_f(float* __restrict__ out, int64_t n, float v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
 }
@@ -63,10 +55,6 @@ __global__ void k_compact(const float* __restrict__ src, float* __restrict__ out
 __global__ void k_expand(const float* __restrict__ src, float* __restrict__ out, int rows, int cols, int ld) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < rows * cols) out[(idx / cols) * ld + (idx % cols)] = src[idx];
-}
-__global__ void k_copy_f(const float* __restrict__ src, float* __restrict__ out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = src[i];
 }
 
 // arma::normalise(X, 2, 0) on the rows of X[n][d] (= columns of the reference's d x N matrix); a zero

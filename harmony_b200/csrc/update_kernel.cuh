@@ -71,24 +71,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned gen = ld_acquire_u32(bar + 1);
-    unsigned arrived;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(bar) : "memory");
-    if (arrived == nblocks - 1) {
-      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
-      __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
-    } else {
-      while (ld_acquire_u32(bar + 1) == gen) __nanosleep(20);
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(UPD_GROUP) : "memory"); }
 
 // ((2E+1)/(O+E+1))^theta (harmony_pow, utils.cpp:84-90) as ex2(theta * lg2(x)): the tables sit on the critical

@@ -140,6 +140,10 @@ int hb_synchronize(hb_handle* h);
 int hb_region_time(hb_handle* h, const char* region, double* ms, int64_t* launches);
 /* Enables per-region CUDA-event timing (adds synchronisation; off by default). */
 int hb_enable_timing(hb_handle* h, int on);
+/* Test hook (host only, no GPU needed): position of cell i (inverse = 0) or the cell at position i
+ * (inverse = 1) in the keyed pseudo-random order of n cells that replaces arma::shuffle (harmony.cpp:272-273)
+ * when no update order is injected.  Returns ~0 for i >= n. */
+uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse);
 
 #ifdef __cplusplus
 }

@@ -123,3 +123,24 @@ def test_harmonize_driver_contract():
         harmonize(Fake(1, status=-1), 3, verbose=False)
     with pytest.raises(RuntimeError, match="non-zero exit status: 7"):
         harmonize(Fake(1, status=7), 3, verbose=False)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 300, 4096, 100003])
+def test_native_update_order_is_a_permutation(n):
+    """The keyed Feistel order that stands in for arma::shuffle (harmony.cpp:272-273) is a bijection of
+    [0, n), its inverse inverts it, different keys give different orders, and blocks come out balanced."""
+    L = _lib.lib()
+    key = 0x1234ABCD
+    pos = np.array([L.hb_debug_permute(i, n, key, 0) for i in range(min(n, 5000))], dtype=np.int64)
+    if n <= 5000:
+        assert sorted(pos.tolist()) == list(range(n))
+    assert pos.min() >= 0 and pos.max() < n and len(set(pos.tolist())) == len(pos)
+    for i in range(0, min(n, 200)):
+        assert L.hb_debug_permute(int(pos[i]), n, key, 1) == i
+    assert L.hb_debug_permute(n, n, key, 0) == 2 ** 64 - 1
+    if n >= 4096:
+        other = np.array([L.hb_debug_permute(i, n, key + 1, 0) for i in range(1000)])
+        assert (other != pos[:1000]).mean() > 0.9
+        blk = np.minimum(pos // (n // 20), 19)           # 20 update blocks as in harmony.cpp:280-300
+        cnt = np.bincount(blk, minlength=20)
+        assert cnt.min() > 0.5 * len(pos) / 20 and cnt.max() < 1.6 * len(pos) / 20
