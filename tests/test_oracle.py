@@ -144,3 +144,59 @@ def test_convergence_semantics():
     assert len(o.trace("objective_kmeans")) == 1 + 4 * iters
     last = (oh[-2] - oh[-1]) / abs(oh[-2])
     assert (last < 1e-2) == (iters < 10 or o.check_convergence(1))
+
+
+def _separated(N=900, d=8, seed=3):
+    """Batches that each hold a cell type of their own (plus one shared type): many (cluster, level) pairs fall
+    below batch_proportion_cutoff, so the level-filter / subset / skip branches of harmony.cpp:358-547 all fire."""
+    rng = np.random.default_rng(seed)
+    batch = rng.integers(0, 3, N)
+    own = rng.random(N) < 0.7
+    ctype = np.where(own, batch, 3)
+    M = rng.standard_normal((4, d)) * 3.0
+    Z = M[ctype] + 0.3 * rng.standard_normal((N, d)) + 0.4 * rng.standard_normal((3, d))[batch]
+    donor = batch * 2 + rng.integers(0, 2, N)
+    return Z, {"batch": batch, "donor": donor}
+
+
+@pytest.mark.parametrize("vars_use", [["batch"], ["batch", "donor"]])
+def test_level_filter_branches_match_numpy(vars_use):
+    Z, meta = _separated()
+    a = _prep(Z, meta, vars_use, nclust=12)
+    K, T, N = a["K"], a["max_iter_kmeans"], Z.shape[0]
+    Y0 = make_Y0(Z, K, 5)
+    perms = make_perms(N, 2 * T, 9).reshape(2, T, N)
+    o64, _, _ = run_oracle(dict(a, epsilon_harmony=-np.inf), Y0, 2, double=True, perms=perms)
+    s = setup_args(a)
+    ref = NumpyHarmony(s["Z"], s["phi_i"], s["B_vec"], s["sigma"], s["theta"], s["lambda_"], s["alpha"], T, K,
+                       s["block_size"], s["batch_proportion_cutoff"])
+    ref.init_cluster(Y0)
+    for it in range(2):
+        ref.cluster(perms[it])
+        ref.moe_correct_ridge()
+    # the filter really fires: some (cluster, level) pairs are below the cutoff, some clusters keep every level
+    avg = ref.O / ref.N_b[None, :]
+    assert (avg <= 1e-5).any() and (avg > 1e-5).all(axis=1).any()
+    assert rel_l2(o64.get("Z_corr"), ref.Z_corr) < 1e-9
+    assert np.abs(o64.get("Y") - ref.Y).max() < 1e-9
+
+
+@pytest.mark.parametrize("N,block_size", [(41, 0.05), (1000, 1.0), (1003, 0.01), (977, 0.3)])
+def test_block_geometry_edge_cases(N, block_size):
+    """n_blocks = my_ceil(1/block_size), cells_per_block = unsigned(N*block_size) in float, last block takes the
+    remainder (harmony.cpp:279-300): one block, 100 blocks, a remainder larger than a block."""
+    Z, meta = synthetic(N, 6, [3], seed=N)
+    a = _prep(Z, meta, "cov0", nclust=4, options=harmony_options(block_size=block_size))
+    T = a["max_iter_kmeans"]
+    Y0 = make_Y0(Z, 4, 1)
+    perms = make_perms(N, T, 2).reshape(1, T, N)
+    o64, _, _ = run_oracle(dict(a, epsilon_harmony=-np.inf), Y0, 1, double=True, perms=perms)
+    s = setup_args(a)
+    ref = NumpyHarmony(s["Z"], s["phi_i"], s["B_vec"], s["sigma"], s["theta"], s["lambda_"], s["alpha"], T, 4,
+                       s["block_size"], s["batch_proportion_cutoff"])
+    ref.init_cluster(Y0)
+    ref.cluster(perms[0])
+    ref.moe_correct_ridge()
+    assert np.abs(o64.get("R") - ref.R).max() < 1e-9
+    assert rel_l2(o64.get("Z_corr"), ref.Z_corr) < 1e-9
+    np.testing.assert_allclose(o64.get("R").sum(axis=1), 1.0, atol=1e-12)
