@@ -190,7 +190,7 @@ def run_reference(args):
     if rank != 0:
         return
     ncpu = os.cpu_count() or 1
-    n_sample = 200_000
+    n_sample = int(args.ref_cells)
     steps = max(1, min(args.steps, 3))
     # the reference only threads its BLAS call (R/ui.R:123-128); time it with all host threads and with the
     # reference default ncores = 1 and report the faster of the two (skinny sgemm often loses with threads)
@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--cells-per-gpu", type=int, default=CELLS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-cells", type=int, default=200_000, help="cells of the bounded CPU sample (--impl reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
