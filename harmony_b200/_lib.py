@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "libharmony_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("harmony_b200.cu", "kernels.cuh", "common.cuh", "update_kernel.cuh",
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("harmony_b200.cu", "kernels.cuh", "common.cuh", "update_kernel.cuh", "update_kernel3.cuh",
                                                      "umma.cuh", "assign_tc.cuh", "stats_tc.cuh", "apply_tc.cuh")]
 HEADER = os.path.join(ROOT, "include", "harmony_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
@@ -92,5 +92,6 @@ def lib():
     L.hb_enable_timing.argtypes = [P, I]
     L.hb_debug_permute.restype = ctypes.c_uint64
     L.hb_debug_permute.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, I]
+    L.hb_debug_update_geometry.argtypes = [I, I, ctypes.POINTER(I64)]
     _LIB = L
     return L

@@ -22,6 +22,7 @@
 
 #include "kernels.cuh"
 #include "update_kernel.cuh"
+#include "update_kernel3.cuh"
 #include "assign_tc.cuh"
 #include "apply_tc.cuh"
 #include "stats_tc.cuh"
@@ -160,6 +161,8 @@ struct hb_handle {
   DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
   int tc_ntiles = 0;
   bool use_tc_assign = false, use_tc_apply = false, use_tc_stats = false;
+  bool use_v3 = false;  // experimental second-generation update kernel (HB_UPDATE_V3=1)
+  Upd3Geom g3{};
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
@@ -635,7 +638,35 @@ int upd_begin_call(hb_handle* h, int T) {
   CK(cudaMemcpyAsync(h->ring.p + 3 * BK, h->E.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   return 0;
 }
+template <int NV>
+int upd3_launch_nv(hb_handle* h, Upd3Args& p, bool cooperative) {
+  const size_t smem = upd3_smem_bytes(h->g3, h->nb);
+  CK(cudaFuncSetAttribute(k_update_steps3<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cooperative) {
+    void* args[] = {&p};
+    CK(cudaLaunchCooperativeKernel((void*)k_update_steps3<NV>, dim3(h->coop_grid), dim3(U3_THREADS), args, smem, h->stream));
+  } else {
+    k_update_steps3<NV><<<h->coop_grid, U3_THREADS, smem, h->stream>>>(p);
+  }
+  CKL();
+  return 0;
+}
+int upd3_launch(hb_handle* h, const UpdArgs& a, bool cooperative) {
+  Upd3Args p;
+  p.a = a;
+  p.a.use_barrier = cooperative ? 1 : 0;
+  p.g = h->g3;
+  switch (h->g3.NV) {
+    case 1: return upd3_launch_nv<1>(h, p, cooperative);
+    case 2: return upd3_launch_nv<2>(h, p, cooperative);
+    case 3: return upd3_launch_nv<3>(h, p, cooperative);
+    case 4: return upd3_launch_nv<4>(h, p, cooperative);
+    case 5: return upd3_launch_nv<5>(h, p, cooperative);
+  }
+  return fail(h, 2, "update kernel v3: unsupported geometry");
+}
 int upd_launch(hb_handle* h, UpdArgs a, bool cooperative) {
+  if (h->use_v3) return upd3_launch(h, a, cooperative);
   const size_t smem = upd_smem_bytes(h);
   return dispatch_nv(h, h->KS, [&](auto nvc) -> int {
     constexpr int NV = decltype(nvc)::value;
@@ -1328,6 +1359,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     h->coop_grid = h->num_sms;  // one persistent CTA per SM
     h->aligned_ranges = (2 * J <= h->coop_grid);
     if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)Tplan * h->nb * h->coop_grid));
+    h->use_v3 = h->aligned_ranges && getenv("HB_UPDATE_V3") != nullptr &&
+                upd3_geometry(KS, h->nb, (size_t)227 * 1024 - 256, &h->g3);  // else: default kernel
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
       CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));
@@ -1760,6 +1793,15 @@ uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse) {
   while ((1ull << bits) < n) bits++;
   const int half_bits = (bits + 1) / 2;
   return inverse ? hb_permute_inv(i, n, half_bits, key) : hb_permute(i, n, half_bits, key);
+}
+
+// Geometry chooser of the experimental update kernel (test hook, host only).
+int hb_debug_update_geometry(int KS, int nb, int64_t out[9]) {
+  Upd3Geom g{};
+  if (KS <= 0 || (KS & 3) || nb <= 0 || !upd3_geometry(KS, nb, (size_t)227 * 1024 - 256, &g)) return 0;
+  const int64_t v[9] = {g.NV, g.LPR, g.RPI, g.IT, g.SR, g.KP, g.DU, g.DL, (int64_t)upd3_smem_bytes(g, nb)};
+  for (int i = 0; i < 9; ++i) out[i] = v[i];
+  return 1;
 }
 
 int hb_enable_timing(hb_handle* h, int on) {

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Validation of the experimental update kernel (HB_UPDATE_V3=1, harmony_b200/csrc/update_kernel3.cuh) on a GPU
+# box: the whole parity suite with the switch on, then the bench with and without it.
+#   gpurun --timeout 1500 -- 'bash scripts/check_v3.sh > gpurun_out/check_v3.log 2>&1'
+set -x
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+HB_UPDATE_V3=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_runharmony.py -x -q -m gpu
+echo "parity exit: $?"
+timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json
+HB_UPDATE_V3=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_v3.json
+HB_UPDATE_V3=1 HB_TRACE_STEPS=0 timeout 300 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null
+python - <<'PY'
+import json
+for n in ("default", "v3"):
+    try:
+        d = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
+        print(n, d["ms_per_step"], d.get("regions_ms_per_step"))
+    except Exception as e:
+        print(n, "failed:", e)
+PY
