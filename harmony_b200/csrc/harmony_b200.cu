@@ -89,6 +89,16 @@ int my_ceil(float num) {
   return inum + 1;
 }
 
+// exchange area of the v3 update kernel (see setup_peer_exchange)
+struct XchArea {
+  int device = 0, world = 0, rank = 0;
+  size_t entries = 0, XH = 0;
+  float* base = nullptr;
+  void* peer[U3_MAXWORLD] = {};
+  unsigned epoch = 0;
+  bool leased = false;
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -163,6 +173,9 @@ struct hb_handle {
   bool use_tc_assign = false, use_tc_apply = false, use_tc_stats = false;
   bool use_v3 = false;  // experimental second-generation update kernel (HB_UPDATE_V3=1)
   Upd3Geom g3{};
+  bool use_xch = false;  // v3 + sharded cells: block steps exchanged through peer memory (HB_PEER_EXCHANGE=1)
+  Upd3Xch xch{};
+  XchArea* xarea = nullptr;  // leased exchange area (process-wide pool, see setup_peer_exchange)
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
@@ -573,6 +586,106 @@ int run_update_R_v1(hb_handle* h, int t) {
   });
 }
 
+// ---- peer-memory exchange area of the v3 update kernel (sharded cells, one node) ------------------
+// Areas live for the life of the process, like the communicators: another rank may still be writing into an
+// area when its owner drops the handle, and unmapping needs a collective that a destructor cannot afford.  A
+// handle leases an area; areas are created collectively, so area i here is paired with area i of every rank.
+constexpr int XCH_MAX_AREAS = 16;
+std::vector<XchArea*> g_xch_areas;
+
+void release_peer_exchange(hb_handle* h) {
+  if (h->xarea) {
+    h->xarea->epoch = h->xch.epoch;  // the next lessee continues the epoch sequence
+    h->xarea->leased = false;
+    h->xarea = nullptr;
+  }
+  h->use_xch = false;
+}
+// Collective over the handle's communicator.  Leases an area all ranks have free, or creates a new one:
+// allocates this rank's part, exchanges the IPC handles and maps the other ranks' parts.  If any rank cannot
+// map a peer the exchange stays off on all ranks (the update then runs one launch + all-reduce per block step).
+int setup_peer_exchange(hb_handle* h, int Tplan) {
+  const int W = h->world;
+  const size_t BK = (size_t)h->B * h->KS, XH = BK + h->KS;
+  const size_t entries = ((size_t)Tplan * h->nb + 2) * 2 * W;
+  // 1. agree on a reusable area: free here AND on every other rank, same shape
+  int64_t freev[XCH_MAX_AREAS + 1];
+  for (int i = 0; i < XCH_MAX_AREAS; ++i) {
+    const XchArea* a = i < (int)g_xch_areas.size() ? g_xch_areas[i] : nullptr;
+    freev[i] = (a && !a->leased && a->device == h->device && a->world == W && a->rank == h->rank && a->entries == entries &&
+                a->XH == XH) ? 1 : 0;
+  }
+  freev[XCH_MAX_AREAS] = -(int64_t)g_xch_areas.size();  // min over ranks = -(largest count): all must be able to add one
+  DevBuf<int64_t> dv;
+  CK(dv.alloc(XCH_MAX_AREAS + 1));
+  CK(cudaMemcpyAsync(dv.p, freev, sizeof(freev), cudaMemcpyHostToDevice, h->stream));
+  CKN(g_nccl.AllReduce(dv.p, dv.p, XCH_MAX_AREAS + 1, ncclInt64, ncclMin, h->comm, h->stream));
+  CK(cudaMemcpyAsync(freev, dv.p, sizeof(freev), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  XchArea* area = nullptr;
+  for (int i = 0; i < XCH_MAX_AREAS && !area; ++i)
+    if (freev[i] == 1) area = g_xch_areas[i];
+  if (!area) {
+    if (-freev[XCH_MAX_AREAS] >= XCH_MAX_AREAS || (int)g_xch_areas.size() != -freev[XCH_MAX_AREAS]) return 0;  // table full / out of step
+    // 2. create a new area (collective)
+    float* base = nullptr;
+    CK(cudaMalloc((void**)&base, sizeof(float) * (entries * XH + entries)));
+    CK(cudaMemsetAsync(base, 0, sizeof(float) * (entries * XH + entries), h->stream));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, base));
+    DevBuf<char> ds, dr;
+    CK(ds.alloc(sizeof(mine)));
+    CK(dr.alloc(sizeof(mine) * W));
+    CK(cudaMemcpyAsync(ds.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllGather(ds.p, dr.p, sizeof(mine), ncclChar, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    CK(cudaMemcpyAsync(all.data(), dr.p, sizeof(mine) * W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    area = new XchArea();
+    area->device = h->device;
+    area->world = W;
+    area->rank = h->rank;
+    area->entries = entries;
+    area->XH = XH;
+    area->base = base;
+    int64_t ok = 1;
+    for (int r = 0; r < W; ++r) {
+      if (r == h->rank) continue;
+      if (cudaIpcOpenMemHandle(&area->peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        area->peer[r] = nullptr;
+        ok = 0;
+      }
+    }
+    CK(cudaMemcpyAsync(dv.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllReduce(dv.p, dv.p, 1, ncclInt64, ncclMin, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&ok, dv.p, sizeof(ok), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    area->leased = !ok;            // an unusable area keeps its index (the ranks stay in step) but is never leased
+    g_xch_areas.push_back(area);
+    if (!ok) {
+      h->warnings.push_back("peer-memory exchange unavailable (CUDA IPC mapping failed); using per-step all-reduce");
+      return 0;
+    }
+  }
+  area->leased = true;
+  h->xarea = area;
+  Upd3Xch& x = h->xch;
+  x.world = W;
+  x.rank = h->rank;
+  x.epoch = area->epoch;
+  x.XH = (int)XH;
+  for (int r = 0; r < W; ++r) {
+    float* base = (r == h->rank) ? area->base : (float*)area->peer[r];
+    x.data[r] = base;
+    x.flag[r] = reinterpret_cast<unsigned*>(base + entries * XH);
+  }
+  x.local_data = x.data[h->rank];
+  x.local_flag = x.flag[h->rank];
+  h->use_xch = true;
+  return 0;
+}
+
 // ---- v2: persistent cooperative kernel over rounds [t0, t1) of this cluster_cpp call --------------
 int nv_for(int KS) {
   int nv = 1;
@@ -631,6 +744,7 @@ UpdArgs make_upd_args(hb_handle* h, int T) {
 // zero the per-step accumulators and seed ring[1] (= "O_{-1}") with the current tables
 int upd_begin_call(hb_handle* h, int T) {
   const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
+  if (h->use_xch) h->xch.epoch++;  // flags of earlier calls no longer match
   CK(cudaMemsetAsync(h->acc2.p, 0, sizeof(float) * SL * ((size_t)T * h->nb + 2), h->stream));
   CK(cudaMemsetAsync(h->obj2.p, 0, sizeof(double) * 2 * (size_t)T, h->stream));
   CK(cudaMemsetAsync(h->bar.p, 0, sizeof(unsigned) * 2 * ((size_t)T * h->nb + 2), h->stream));
@@ -656,6 +770,7 @@ int upd3_launch(hb_handle* h, const UpdArgs& a, bool cooperative) {
   p.a = a;
   p.a.use_barrier = cooperative ? 1 : 0;
   p.g = h->g3;
+  if (h->use_xch) p.x = h->xch;
   switch (h->g3.NV) {
     case 1: return upd3_launch_nv<1>(h, p, cooperative);
     case 2: return upd3_launch_nv<2>(h, p, cooperative);
@@ -695,7 +810,7 @@ int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
   const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
   UpdArgs a = make_upd_args(h, T);
   a.write_R_mask = write_mask;
-  if (h->world <= 1) {
+  if (h->world <= 1 || h->use_xch) {
     a.s_begin = t0 * nb;
     a.s_end = t1 * nb;
     a.prologue = (t0 == 0) ? 1 : 0;
@@ -739,7 +854,10 @@ int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
   // tables at the end of round t1-1 -> O, E (the chain itself continues from the ring)
   {
     RegionScope r4(h, "k_update_finalize");
-    k_update_finalize<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
+    if (h->use_xch)
+      k_update_finalize3<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, h->xch, t1 * nb, h->O.p, h->E.p);
+    else
+      k_update_finalize<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
     CKL();
   }
   // compute_objective() of every round in [t0, t1) (harmony.cpp:248)
@@ -1020,6 +1138,7 @@ void hb_destroy(hb_handle* h) {
   if (h->plan_done) cudaEventDestroy(h->plan_done);
   if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
+  release_peer_exchange(h);
   cudaStream_t s = h->stream;
   delete h;  // frees device buffers
   if (s) cudaStreamDestroy(s);
@@ -1361,6 +1480,9 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)Tplan * h->nb * h->coop_grid));
     h->use_v3 = h->aligned_ranges && getenv("HB_UPDATE_V3") != nullptr &&
                 upd3_geometry(KS, h->nb, (size_t)227 * 1024 - 256, &h->g3);  // else: default kernel
+    release_peer_exchange(h);
+    if (h->use_v3 && h->world > 1 && h->world <= U3_MAXWORLD && getenv("HB_PEER_EXCHANGE") != nullptr)
+      TRY(setup_peer_exchange(h, Tplan));
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
       CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));

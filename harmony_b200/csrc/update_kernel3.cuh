@@ -39,10 +39,68 @@ struct Upd3Geom {
   int DU, DL;  // ring depths (stages) of the update / look-ahead group
 };
 
+// Multi-GPU step exchange through peer memory (one process per GPU, cells sharded).  Every rank
+// owns an exchange area that all ranks of the node have mapped (CUDA IPC over NVLink):
+//   data[((slot * 2 + half) * world + src) * XH + i]     flags[(slot * 2 + half) * world + src]
+// slot = s + 1 for the accumulator slot of step s, half 0 = add_{s-1}, half 1 = rem_s (XH = B KS + KS floats).
+// The CTA that completes a half of the LOCAL accumulator slot copies it into entry `src = rank` of every
+// rank's area and then raises the flags (value = epoch of the running cluster_cpp call).  Readers wait for
+// the `world` flags of a half and add the partial sums in rank order, so every rank derives bit-identical
+// tables without a collective launch between block steps.
+constexpr int U3_MAXWORLD = 8;
+struct Upd3Xch {
+  int world = 1, rank = 0;
+  unsigned epoch = 0;
+  int XH = 0;
+  float* local_data = nullptr;
+  unsigned* local_flag = nullptr;
+  float* data[U3_MAXWORLD] = {};
+  unsigned* flag[U3_MAXWORLD] = {};
+};
+
 struct Upd3Args {
   UpdArgs a;
   Upd3Geom g;
+  Upd3Xch x;
 };
+
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// sum over the ranks' partial sums of element `off` of (slot, half), in rank order
+__device__ __forceinline__ float u3_xsum(const Upd3Xch& x, int slot, int half, int off) {
+  const float* q = x.local_data + ((size_t)(slot * 2 + half) * x.world) * x.XH + off;
+  float t = 0.f;
+  for (int r = 0; r < x.world; ++r) t += __ldcg(q + (size_t)r * x.XH);
+  return t;
+}
+// derive() for sharded cells: the accumulator terms are sums over the ranks' exchange entries.  s is the
+// step within the call: slot(s - 1) and the add half of slot(s) do not exist for s == 0 (zero).
+__device__ __forceinline__ void derive_x(const Upd3Xch& x, const TableView& tv, const float* Pr_b, const float* theta, int s,
+                                         int b, int k, bool with_removal, float& o, float& e, float& p) {
+  const int idx = b * tv.KS + k;
+  const float prb = Pr_b[b];
+  float prev_rem_O = 0.f, prev_rem_rs = 0.f, cur_add_O = 0.f, cur_add_rs = 0.f;
+  if (s >= 1) {
+    prev_rem_O = u3_xsum(x, s, 1, idx);
+    prev_rem_rs = u3_xsum(x, s, 1, tv.BK + k);
+    cur_add_O = u3_xsum(x, s + 1, 0, idx);
+    cur_add_rs = u3_xsum(x, s + 1, 0, tv.BK + k);
+  }
+  o = (__ldcg(tv.ringO + idx) - prev_rem_O) + cur_add_O;
+  e = (__ldcg(tv.ringE + idx) - prev_rem_rs * prb) + cur_add_rs * prb;
+  p = 0.f;
+  if (with_removal) {
+    const float e_eff = e - u3_xsum(x, s + 1, 1, tv.BK + k) * prb;
+    const float o_eff = o - u3_xsum(x, s + 1, 1, idx);
+    p = penalty_pow(o_eff, e_eff, theta[b]);
+  }
+}
 
 // shared-memory carve-up (floats): sig[KP] | tabU[2 KP] | tabL[(nb+1) KP] | partU[NWU KP] | partL[NWL KP] |
 //   metaU[DU 32] | metaL[DL 32] | mbarriers[2 DU + 2 DL] (8 B each) | ringU[DU SR KP] | ringL[DL SR KP]
@@ -124,6 +182,8 @@ template <int NV>
 __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
   extern __shared__ __align__(16) float smem[];
   const UpdArgs& a = p.a;
+  const Upd3Xch& x = p.x;
+  const bool multi = x.world > 1;
   const int K = a.K, KS = a.KS, C = a.C, B = a.B, nb = a.nb;
   const int LPR = p.g.LPR, RPI = p.g.RPI, SR = p.g.SR, KP = p.g.KP, DU = p.g.DU, DL = p.g.DL;
   const int BK = B * KS;
@@ -145,6 +205,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
   float* ringU = reinterpret_cast<float*>(emptyL + DL);
   float* ringL = ringU + (size_t)DU * SR * KP;
   __shared__ double sh_obj[2];
+  __shared__ int sh_last[2];  // per consumer group: this CTA completed the half it just signalled
 
   // ---- one-time initialisation: zero everything that is read before it is written (stale stage rows are
   // consumed with weight 0 and must be finite), tables' padding columns stay 0 for the whole kernel
@@ -249,11 +310,35 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
   const uint32_t lane_off = (uint32_t)(rgc * KP + gl * 4) * 4u;  // byte offset of the lane's first slot in an iteration
   const uint32_t it_stride = (uint32_t)(RPI * KP) * 4u;  // bytes between warp iterations of a stage
   auto gsync = [&]() { umma::named_sync(bar_id, GT); };
-  auto signal = [&](unsigned* c) {
+  // signal(c, slot, half): this CTA's group is done with the step counted by c; with sharded cells the CTA that
+  // completes the count publishes the finished half (slot, half) of the local accumulators to every rank
+  auto signal = [&](unsigned* c, int slot, int half) {
     gsync();
+    if (!multi) {
+      if (gt == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+      }
+      return;
+    }
     if (gt == 0) {
       __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+      const unsigned old = atomicAdd(c, 1u);
+      __threadfence();
+      sh_last[isU ? 0 : 1] = (old == (unsigned)grid - 1u) ? 1 : 0;
+    }
+    gsync();
+    if (sh_last[isU ? 0 : 1]) {
+      const float* src = a.acc + (size_t)slot * SL + (size_t)half * x.XH;  // complete: every CTA's atomics preceded its count
+      const size_t entry = ((size_t)(slot * 2 + half) * x.world + x.rank);
+      for (int r = 0; r < x.world; ++r) {
+        float* dst = x.data[r] + entry * x.XH;
+        for (int i = gt * 4; i < x.XH; i += GT * 4)
+          *reinterpret_cast<float4*>(dst + i) = __ldcg(reinterpret_cast<const float4*>(src + i));
+      }
+      __threadfence_system();
+      gsync();
+      if (gt < x.world) st_release_sys_u32(x.flag[gt] + entry, x.epoch);
     }
   };
   auto wait_for = [&](const unsigned* c) {
@@ -262,6 +347,22 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
       __threadfence();
     }
     gsync();
+  };
+  // sharded cells: all ranks' entries of (slot, half) have arrived in the local exchange area
+  auto wait_half = [&](int slot, int half) {
+    if (gt < x.world) {
+      const unsigned* f = x.local_flag + (size_t)(slot * 2 + half) * x.world + gt;
+      while (ld_acquire_sys_u32(f) != x.epoch) __nanosleep(40);
+      __threadfence();
+    }
+    gsync();
+  };
+  // O_s, E_s (and P_s) of element (b, k) from the local or the exchanged accumulators
+  auto derive_any = [&](const TableView& tv, int s, int b, int k, float& o, float& e, float& pp) {
+    if (multi)
+      derive_x(x, tv, a.Pr_b, a.theta, s, b, k, true, o, e, pp);
+    else
+      derive(tv, a.Pr_b, a.theta, b, k, o, e, pp);
   };
   auto stamp = [&](int s, int slot_id) {
     if (a.dbg && cta == a.dbg_cta && gt == 0) {
@@ -334,7 +435,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
       for (int idx = cta * GT + gt; idx < BK; idx += grid * GT) {
         const int b = idx / KS, k = idx - b * KS;
         float o = 0.f, e = 0.f, pp = 0.f;
-        if (k < K) derive(tv, a.Pr_b, a.theta, b, k, o, e, pp);
+        if (k < K) derive_any(tv, s, b, k, o, e, pp);
         outO[idx] = o;
         outE[idx] = e;
         Ps[idx] = pp;
@@ -358,6 +459,13 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
       if (a.use_barrier) {
         if (s > a.s_begin) wait_for(cntU + s - 1);            // add_{s-1}, ring, Psave of step s-1
         if (s > a.s_begin || a.prologue) wait_for(cntL + s);  // rem_s
+        if (multi) {  // the other ranks' shares of add_{s-1}, rem_{s-1} and rem_s
+          if (s >= 1) {
+            wait_half(s + 1, 0);
+            wait_half(s, 1);
+          }
+          wait_half(s + 1, 1);
+        }
       }
       stamp(s, 1);
       if (nst > 0) {
@@ -369,7 +477,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
             if (k < K)
               for (int c = 0; c < C; ++c) {
                 float o, e, pp;
-                derive(tv, a.Pr_b, a.theta, __ldg(a.tuple_levels + q * C + c), k, o, e, pp);
+                derive_any(tv, s, __ldg(a.tuple_levels + q * C + c), k, o, e, pp);
                 v += pp;
               }
             tabU[k] = v;
@@ -491,7 +599,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
       owners(s);
       if ((s + 1) % nb == 0) flush_objective(s / nb);
       stamp(s, 6);
-      if (a.use_barrier) signal(cntU + s);
+      if (a.use_barrier) signal(cntU + s, s + 2, 0);  // add_s is half 0 of slot(s + 1)
       gbase += nst;
     }
     if (a.s_end % nb != 0 && a.s_end > a.s_begin) flush_objective((a.s_end - 1) / nb);  // partial round
@@ -605,9 +713,36 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
         flush(partL, q, slot_s + BK + KS, slot_s + 2 * BK + KS);
         stamp(s - 1, 5);
       }
-      if (a.use_barrier) signal(cntL + s);
+      if (a.use_barrier) signal(cntL + s, s + 1, 1);  // rem_s is half 1 of slot(s)
       gbase += nst;
     }
+  }
+}
+
+// k_update_finalize for sharded cells with the peer-memory exchange: O = O_S, E = E_S from the exchanged
+// partial sums (waits for the last halves of the other ranks, whose kernels may still be running).
+__global__ void k_update_finalize3(UpdArgs a, Upd3Xch x, int S, float* __restrict__ O, float* __restrict__ E) {
+  const int KS = a.KS, BK = a.B * KS;
+  if (S >= 1 && (int)threadIdx.x < x.world) {
+    const unsigned* f0 = x.local_flag + (size_t)((S + 1) * 2 + 0) * x.world + threadIdx.x;  // add_{S-1}
+    const unsigned* f1 = x.local_flag + (size_t)(S * 2 + 1) * x.world + threadIdx.x;        // rem_{S-1}
+    while (ld_acquire_sys_u32(f0) != x.epoch) __nanosleep(40);
+    while (ld_acquire_sys_u32(f1) != x.epoch) __nanosleep(40);
+    __threadfence();
+  }
+  __syncthreads();
+  TableView tv;
+  tv.ringO = a.ring + (size_t)((S - 1) & 1) * 2 * BK;
+  tv.ringE = tv.ringO + BK;
+  tv.prev = tv.cur = nullptr;
+  tv.BK = BK;
+  tv.KS = KS;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < BK; idx += gridDim.x * blockDim.x) {
+    const int b = idx / KS, k = idx - b * KS;
+    float o = 0.f, e = 0.f, pp;
+    if (k < a.K) derive_x(x, tv, a.Pr_b, a.theta, S, b, k, false, o, e, pp);
+    O[idx] = o;
+    E[idx] = e;
   }
 }
 
