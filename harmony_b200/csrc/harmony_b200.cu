@@ -609,24 +609,26 @@ int setup_peer_exchange(hb_handle* h, int Tplan) {
   const size_t BK = (size_t)h->B * h->KS, XH = BK + h->KS;
   const size_t entries = ((size_t)Tplan * h->nb + 2) * 2 * W;
   // 1. agree on a reusable area: free here AND on every other rank, same shape
-  int64_t freev[XCH_MAX_AREAS + 1];
+  int64_t freev[XCH_MAX_AREAS + 2];
   for (int i = 0; i < XCH_MAX_AREAS; ++i) {
     const XchArea* a = i < (int)g_xch_areas.size() ? g_xch_areas[i] : nullptr;
     freev[i] = (a && !a->leased && a->device == h->device && a->world == W && a->rank == h->rank && a->entries == entries &&
                 a->XH == XH) ? 1 : 0;
   }
-  freev[XCH_MAX_AREAS] = -(int64_t)g_xch_areas.size();  // min over ranks = -(largest count): all must be able to add one
+  freev[XCH_MAX_AREAS] = (int64_t)g_xch_areas.size();       // min over ranks = smallest pool ...
+  freev[XCH_MAX_AREAS + 1] = -(int64_t)g_xch_areas.size();  // ... and -(largest pool): they must agree
   DevBuf<int64_t> dv;
-  CK(dv.alloc(XCH_MAX_AREAS + 1));
+  CK(dv.alloc(XCH_MAX_AREAS + 2));
   CK(cudaMemcpyAsync(dv.p, freev, sizeof(freev), cudaMemcpyHostToDevice, h->stream));
-  CKN(g_nccl.AllReduce(dv.p, dv.p, XCH_MAX_AREAS + 1, ncclInt64, ncclMin, h->comm, h->stream));
+  CKN(g_nccl.AllReduce(dv.p, dv.p, XCH_MAX_AREAS + 2, ncclInt64, ncclMin, h->comm, h->stream));
   CK(cudaMemcpyAsync(freev, dv.p, sizeof(freev), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   XchArea* area = nullptr;
   for (int i = 0; i < XCH_MAX_AREAS && !area; ++i)
     if (freev[i] == 1) area = g_xch_areas[i];
   if (!area) {
-    if (-freev[XCH_MAX_AREAS] >= XCH_MAX_AREAS || (int)g_xch_areas.size() != -freev[XCH_MAX_AREAS]) return 0;  // table full / out of step
+    // every rank sees the same reduced values, so every rank takes the same branch here
+    if (freev[XCH_MAX_AREAS] != -freev[XCH_MAX_AREAS + 1] || freev[XCH_MAX_AREAS] >= XCH_MAX_AREAS) return 0;  // out of step / pool full
     // 2. create a new area (collective)
     float* base = nullptr;
     CK(cudaMalloc((void**)&base, sizeof(float) * (entries * XH + entries)));

@@ -147,8 +147,6 @@ inline bool upd3_geometry(int KS, int nb, size_t smem_limit, Upd3Geom* out) {
   return true;
 }
 
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -206,6 +204,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
   float* ringL = ringU + (size_t)DU * SR * KP;
   __shared__ double sh_obj[2];
   __shared__ int sh_last[2];  // per consumer group: this CTA completed the half it just signalled
+  __shared__ int sh_tick[2][4];  // per group and step (mod 4): next stage of the step to hand to a consumer warp
 
   // ---- one-time initialisation: zero everything that is read before it is written (stale stage rows are
   // consumed with weight 0 and must be finite), tables' padding columns stay 0 for the whole kernel
@@ -227,6 +226,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
     umma::fence_barrier_init();
     sh_obj[0] = 0.0;
     sh_obj[1] = 0.0;
+    for (int i = 0; i < 4; ++i) sh_tick[0][i] = sh_tick[1][i] = 0;
   }
   __syncthreads();
 
@@ -310,6 +310,20 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
   const uint32_t lane_off = (uint32_t)(rgc * KP + gl * 4) * 4u;  // byte offset of the lane's first slot in an iteration
   const uint32_t it_stride = (uint32_t)(RPI * KP) * 4u;  // bytes between warp iterations of a stage
   auto gsync = [&]() { umma::named_sync(bar_id, GT); };
+  // Stages of a step are handed out dynamically (the rows per CTA and step rarely divide evenly among the
+  // warps).  The counter of step s is re-armed two steps earlier, when every warp of the group has left step s - 4.
+  // Only min(warps, ring depth) warps take stages: with more, a warp could wait for the second refill of a slot
+  // whose first refill is still outstanding, and an mbarrier phase parity cannot tell those two apart.
+  int* tick = sh_tick[isU ? 0 : 1];
+  const bool takes_stages = gw < (isU ? DU : DL);
+  auto next_stage = [&](int s) {
+    int i = 0x7fffffff;
+    if (takes_stages) {
+      if (lane == 0) i = atomicAdd(tick + (s & 3), 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+    }
+    return i;
+  };
   // signal(c, slot, half): this CTA's group is done with the step counted by c; with sharded cells the CTA that
   // completes the count publishes the finished half (slot, half) of the local accumulators to every rank
   auto signal = [&](unsigned* c, int slot, int half) {
@@ -384,16 +398,16 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float x = lane_on ? cs[v][c] : 0.f;
+        float col = lane_on ? cs[v][c] : 0.f;
 #pragma unroll
         for (int m = 1; m < 32; m <<= 1) {
           if (m < RPI) {  // warp-uniform: fold row group rg + m onto rg
-            const float y = __shfl_down_sync(0xffffffffu, x, (unsigned)(m * LPR) & 31u);
-            if (rg + m < RPI) x += y;
+            const float y = __shfl_down_sync(0xffffffffu, col, (unsigned)(m * LPR) & 31u);
+            if (rg + m < RPI) col += y;
           }
         }
         cs[v][c] = 0.f;
-        if (lane < LPR) part[(size_t)gw * KP + (gl + LPR * v) * 4 + c] = x;
+        if (lane < LPR) part[(size_t)gw * KP + (gl + LPR * v) * 4 + c] = col;
       }
     gsync();
     for (int k = gt; k < K; k += GT) {
@@ -450,6 +464,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
     int gbase = 0;  // stages consumed by the group before this step (same count as the producer's)
     for (int s = a.s_begin; s < a.s_end; ++s) {
       stamp(s, 0);
+      if (gt == 0) tick[(s + 2) & 3] = 0;
       int lo, hi, q;
       range_of(s, lo, hi, q);
       const int nrows = hi - lo;
@@ -492,7 +507,6 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
           pP[v] = *reinterpret_cast<const float4*>(tabU + (gl + LPR * v) * 4);
           if (!lane_on) pP[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        int pending = -1;  // slot whose bulk stores (R rows) may still be reading the stage
         const uint32_t tabU_l = umma::smem_u32(tabU) + (uint32_t)gl * 16u;          // Psum slots of this lane
         const uint32_t tabLg_l = tabU_l + (uint32_t)KP * 4u;                         // log Psum slots
         const uint32_t sig_l = umma::smem_u32(sig) + (uint32_t)gl * 16u;
@@ -517,14 +531,14 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float x = fast_exp(uu[c]) * pp[c];  // un-normalised R (>= 0)
-              ep[v][c] = x;
-              ssum += x;
+              const float xr = fast_exp(uu[c]) * pp[c];  // un-normalised R (>= 0)
+              ep[v][c] = xr;
+              ssum += xr;
               if constexpr (SIGU) {
-                Aacc = fmaf(x, uu[c], Aacc);
-                Bacc = fmaf(x, ll[c], Bacc);
+                Aacc = fmaf(xr, uu[c], Aacc);
+                Bacc = fmaf(xr, ll[c], Bacc);
               } else {
-                const float tt = sg[c] * x;
+                const float tt = sg[c] * xr;
                 Aacc = fmaf(tt, uu[c], Aacc);
                 Bacc = fmaf(tt, ll[c], Bacc);
                 Sacc += tt;
@@ -555,7 +569,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
             oent = fmaf(inv, (Aacc + Bacc) - ls * Sacc, oent);
           }
         };
-        for (int i = gw; i < nst; i += U3_NWU) {
+        for (int i = next_stage(s); i < nst; i = next_stage(s)) {
           const int g = gbase + i;
           const int slot = g % DU, use = g / DU;
           umma::mbar_wait(fullU + slot, use & 1);
@@ -575,21 +589,12 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
             __syncwarp();
             if (lane < nr) umma::bulk_store(a.R + (size_t)metaU[slot * 32 + lane] * KS, sbase + (size_t)lane * KP, row_bytes);
             umma::bulk_commit();
-            if (pending >= 0) {
-              bulk_wait_read1();  // all but the newest group have been read
-              __syncwarp();
-              if (lane == 0) umma::mbar_arrive(emptyU + pending);
-            }
-            pending = slot;
-          } else {
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(emptyU + slot);
+            // A warp never holds a stage while it waits for another one (the producer refills in order, so a
+            // held slot could be the very slot the next stage needs): wait until the stores have read the rows.
+            umma::bulk_wait_read();
           }
-        }
-        if (pending >= 0) {
-          umma::bulk_wait_read();
           __syncwarp();
-          if (lane == 0) umma::mbar_arrive(emptyU + pending);
+          if (lane == 0) umma::mbar_arrive(emptyU + slot);
         }
         stamp(s, 4);
         float* nslot = a.acc + (size_t)(s + 2) * SL;  // slot(s+1): add_s goes to its addprev part
@@ -616,6 +621,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
       const int nst = (nrows + SR - 1) / SR;
       const int t = s / nb;
       const bool fromR = (s < nb) && a.first_round_from_R;
+      if (gt == 0) tick[(s + 2) & 3] = 0;
       stamp(s - 1, 1);
       if (a.use_barrier) {
         int need = (t > 0) ? t * nb - 1 : -1;  // the previous round's tables must all be saved
@@ -657,7 +663,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
         stamp(s - 1, 3);
         const uint32_t tabL_l = umma::smem_u32(tabL) + (uint32_t)gl * 16u;
         const uint32_t tab_row = (uint32_t)KP * 4u;
-        for (int i = gw; i < nst; i += U3_NWL) {
+        for (int i = next_stage(s); i < nst; i = next_stage(s)) {
           const int g = gbase + i;
           const int slot = g % DL, use = g / DL;
           umma::mbar_wait(fullL + slot, use & 1);
