@@ -7,6 +7,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -80,6 +82,25 @@ std::map<CommKey, ncclComm_t> g_comms;
 struct Region {
   double ms = 0;
   int64_t launches = 0;
+};
+
+// Host-side phase timer for the one-off calls (HB_TRACE_HOST=1): every mark() drains the stream and prints the
+// wall-clock time since the previous mark to stderr.  Off: a single branch per mark.
+struct HostLap {
+  cudaStream_t stream;
+  const char* call;
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  HostLap(cudaStream_t s, const char* c) : stream(s), call(c), on(getenv("HB_TRACE_HOST") != nullptr) {
+    if (on) t = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hb] %s: %-28s %9.3f ms\n", call, what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
 };
 
 // utils.cpp:102-108
@@ -1275,6 +1296,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     h->half_bits = (bits + 1) / 2;
   }
 
+  HostLap lap(h->stream, "hb_setup");
   // ---- joint covariate tuples; cells get sorted by tuple (stable)
   std::vector<int64_t> lvl_count(B, 0);
   std::vector<uint64_t> key(N);
@@ -1415,6 +1437,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   for (int q = J - 1; q >= 0; --q)
     if (tstart[q + 1] == tstart[q]) t_chunk0[q] = (q + 1 < J) ? t_chunk0[q + 1] : h->nchunks - 1;
 
+  lap.mark("tuple dictionary / sort (host)");
   // ---- device allocations
   const int KS = h->KS, DS = h->DS;
   const size_t nK = (size_t)N * KS, nd = (size_t)N * DS, BK = (size_t)B * KS;
@@ -1493,6 +1516,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(cudaMemsetAsync(h->Psave.p, 0, sizeof(float) * 2 * (size_t)h->nb * BK, h->stream));
     CK(cudaMemsetAsync(h->ring.p, 0, sizeof(float) * 4 * BK, h->stream));
   }
+  lap.mark("device allocations");
   CK(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
   CK(cudaMemsetAsync(h->O.p, 0, sizeof(float) * BK, h->stream));
@@ -1542,11 +1566,13 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(cudaStreamSynchronize(h->stream));
   }
 #undef UP
+  lap.mark("memsets + small uploads");
   // Z: double -> float, into tuple-sorted order (harmony.cpp:41); Z_corr = normalise(Z_orig) (:42)
   TRY(upload_rows(h, Z, d, h->DS, h->Zo.p));
   k_normalise_rows<<<grid_for(N * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->Zo.p, h->Zc.p, N, d, h->DS);
   CKL();
   CK(cudaStreamSynchronize(h->stream));
+  lap.mark("Z upload + normalise");
   h->ran_setup = true;
   return 0;
 }
@@ -1555,6 +1581,7 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
   if (!h) return 1;
   if (!h->ran_setup) return fail(h, 3, "setup has not been run");
   CK(cudaSetDevice(h->device));
+  HostLap lap(h->stream, "hb_init_cluster");
   if (Y0) {
     // Y = normalise(kmeans_centers(..)) (harmony.cpp:133-136), centroids injected by the caller
     TRY(upload_small(h, Y0, (size_t)h->K * h->d, h->Y.p));
@@ -1586,11 +1613,13 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
     CK(cudaStreamSynchronize(h->stream));
   }
   // Y = arma::normalise(Y, 2, 0)  (harmony.cpp:136)
+  lap.mark("centroids (Y0 / native k-means)");
   k_normalise_rows<<<grid_for((int64_t)h->K * 32, 256, 64), 256, 0, h->stream>>>(h->Y.p, h->Y.p, h->K, h->d, h->d);
   CKL();
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
   TRY(run_assign(h, false));
   TRY(push_objective(h));                       // compute_objective() (:152)
+  lap.mark("assignment + objective");
   h->harmony_slots.push_back(h->obj_count - 1);  // objective_harmony.push_back (:153)
   h->ran_init = true;
   return 0;
@@ -1761,7 +1790,12 @@ int hb_get_field(hb_handle* h, int field, double* out) {
   CK(cudaSetDevice(h->device));
   const int K = h->K, B = h->B, d = h->d;
   switch (field) {
-    case HB_Z_CORR: return download_rows(h, h->Zc.p, d, h->DS, out);
+    case HB_Z_CORR: {
+      HostLap lap(h->stream, "hb_get_field");
+      const int rc = download_rows(h, h->Zc.p, d, h->DS, out);
+      lap.mark("Z_corr download");
+      return rc;
+    }
     case HB_Z_ORIG: return download_rows(h, h->Zo.p, d, h->DS, out);
     case HB_R: return download_rows(h, h->R.p, K, h->KS, out);
     case HB_Y: return download_small(h, h->Y.p, (size_t)K * d, out);
