@@ -27,7 +27,9 @@
 #include "update_kernel3.cuh"
 #include "assign_tc.cuh"
 #include "apply_tc.cuh"
+#include "apply_tc2.cuh"
 #include "stats_tc.cuh"
+#include "stats_tc2.cuh"
 
 namespace {
 
@@ -913,10 +915,17 @@ int run_correct(hb_handle* h) {
       t.KS = h->KS;
       t.DS = h->DS;
       t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
-      const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
-      CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
       const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
-      k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+      static const bool stats_v2 = getenv("HB_STATS_V2") != nullptr;  // experimental 3-stage variant
+      if (stats_v2 && stats_tc2_smem_bytes(h->KS, h->DS) <= 227 * 1024) {
+        const size_t smem_tc = stats_tc2_smem_bytes(h->KS, h->DS);
+        CK(cudaFuncSetAttribute(k_stats_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        k_stats_tc2<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+      } else {
+        const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
+        CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+      }
       CKL();
     } else {
     StatsArgs a;
@@ -997,10 +1006,17 @@ int run_correct(hb_handle* h) {
       CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 64 * 12, h->stream));
       a.dbg = h->dbg.p;
     }
-    const size_t smem = apply_tc_smem_bytes(a.KD, h->KS);
-    CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
+    static const bool apply_v2 = getenv("HB_APPLY_V2") != nullptr;  // experimental deeper-ring variant
+    if (apply_v2 && apply_tc2_smem_bytes(a.KD, h->KS) <= 227 * 1024) {
+      const size_t smem = apply_tc2_smem_bytes(a.KD, h->KS);
+      CK(cudaFuncSetAttribute(k_apply_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_apply_tc2<<<grid, AP_THREADS, smem, h->stream>>>(a);
+    } else {
+      const size_t smem = apply_tc_smem_bytes(a.KD, h->KS);
+      CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
+    }
     CKL();
     if (tracing) {
       std::vector<long long> st(64 * 12);

@@ -9,10 +9,15 @@ HB_UPDATE_V3=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_
 echo "parity exit: $?"
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json
 HB_UPDATE_V3=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_v3.json
+for sw in HB_APPLY_V2 HB_STATS_V2; do   # the deeper-ring variants of the ridge kernels, one at a time
+  env $sw=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_run or stepwise"
+  echo "$sw parity exit: $?"
+  env $sw=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_$sw.json
+done
 HB_UPDATE_V3=1 HB_TRACE_STEPS=0 timeout 300 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null
 python - <<'PY'
 import json
-for n in ("default", "v3"):
+for n in ("default", "v3", "HB_APPLY_V2", "HB_STATS_V2"):
     try:
         d = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
         print(n, d["ms_per_step"], d.get("regions_ms_per_step"))
