@@ -7,7 +7,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include <algorithm>
 #include <cmath>
@@ -85,6 +89,94 @@ struct Region {
   double ms = 0;
   int64_t launches = 0;
 };
+
+// ---- host worker pool: widens float -> double into caller memory with several threads ---------------------
+// A device -> host copy into pageable memory runs at the speed of one driver thread that also takes the page
+// faults of a freshly allocated destination.  The threaded download path (HB_DOWNLOAD_MT=1) instead DMA's
+// floats into pinned staging and lets this pool widen + scatter them while the next chunk is in flight.
+class WidenPool {
+ public:
+  explicit WidenPool(int nthreads) {
+    for (int i = 1; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~WidenPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_job_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int threads() const { return (int)workers_.size() + 1; }
+  // dst[i] = (double) src[i], i < n; the caller takes part
+  void widen(double* dst, const float* src, size_t n) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      dst_ = dst;
+      src_ = src;
+      n_ = n;
+      next_.store(0);
+      pending_ = (int)workers_.size();
+      ++gen_;
+    }
+    cv_job_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  static constexpr size_t kSlice = (size_t)1 << 18;  // elements per grab (2 MiB of doubles)
+  void work() {
+    for (;;) {
+      const size_t i0 = next_.fetch_add(kSlice);
+      if (i0 >= n_) break;
+      const size_t i1 = std::min(n_, i0 + kSlice);
+      for (size_t i = i0; i < i1; ++i) dst_[i] = (double)src_[i];
+    }
+  }
+  void run() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_job_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_job_, cv_done_;
+  double* dst_ = nullptr;
+  const float* src_ = nullptr;
+  size_t n_ = 0;
+  std::atomic<size_t> next_{0};
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+WidenPool* widen_pool(int want = 0) {
+  static std::mutex mk;
+  static WidenPool* pool = nullptr;
+  std::lock_guard<std::mutex> lk(mk);
+  if (!pool) {
+    int n = want;
+    if (n <= 0) {
+      const char* e = getenv("HB_HOST_THREADS");
+      n = e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    }
+    pool = new WidenPool(std::max(1, n));  // lives until the process exits
+  }
+  return pool;
+}
 
 // Host-side phase timer for the one-off calls (HB_TRACE_HOST=1): every mark() drains the stream and prints the
 // wall-clock time since the previous mark to stderr.  Off: a single branch per mark.
@@ -1077,7 +1169,65 @@ int check_err_flag(hb_handle* h) {
 }
 
 // rows of a per-cell field (device row stride ld), un-sorted and widened to double, via a bounded staging buffer
+// Threaded variant (HB_DOWNLOAD_MT=1): rows are gathered on the device as floats (half the PCIe bytes), DMA'd
+// into two pinned staging buffers and widened into the caller's array by the host pool while the next chunk is
+// in flight.  The pinned buffers live for the life of the process.
+int download_rows_mt(hb_handle* h, const float* src, int cols, int ld, double* out, bool* done) {
+  static float* pinned[2] = {nullptr, nullptr};
+  static const size_t kFloats = (size_t)8 << 20;  // 32 MiB per buffer
+  *done = false;
+  if (!pinned[0]) {
+    for (int i = 0; i < 2; ++i)
+      if (cudaHostAlloc((void**)&pinned[i], sizeof(float) * kFloats, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        if (i == 1) cudaFreeHost(pinned[0]);
+        pinned[0] = pinned[1] = nullptr;
+        return 0;  // no pinned memory: the caller falls back to the plain path
+      }
+  }
+  WidenPool* pool = widen_pool();
+  const int64_t n = h->n;
+  float* dev = reinterpret_cast<float*>(h->stage.p);  // two halves of the device staging buffer
+  const size_t dev_half = std::min(kFloats, h->stage.n);  // stage.n doubles = 2 * stage.n floats
+  const int64_t rows_per = std::max<int64_t>(1, (int64_t)(dev_half / (size_t)cols));
+  const int64_t nchunks = (n + rows_per - 1) / rows_per;
+  cudaEvent_t ev[2];
+  CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  auto enqueue = [&](int64_t i) -> int {
+    const int64_t r0 = i * rows_per, rows = std::min(rows_per, n - r0);
+    float* d = dev + (size_t)(i & 1) * dev_half;
+    k_download_rows_f<<<grid_for(rows * cols, 256, h->num_sms * 8), 256, 0, h->stream>>>(src, d, h->inv_sort.p, r0, rows,
+                                                                                         cols, ld);
+    CKL();
+    CK(cudaMemcpyAsync(pinned[i & 1], d, sizeof(float) * (size_t)rows * cols, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(ev[i & 1], h->stream));
+    return 0;
+  };
+  int rc = nchunks > 0 ? enqueue(0) : 0;
+  for (int64_t i = 0; i < nchunks && rc == 0; ++i) {
+    if (i + 1 < nchunks) rc = enqueue(i + 1);  // its buffers were released by widen(i - 1)
+    if (rc) break;
+    if (cudaEventSynchronize(ev[i & 1]) != cudaSuccess) {
+      rc = fail(h, 10, "CUDA error while downloading rows");
+      break;
+    }
+    const int64_t r0 = i * rows_per, rows = std::min(rows_per, n - r0);
+    pool->widen(out + r0 * cols, pinned[i & 1], (size_t)rows * cols);
+  }
+  cudaStreamSynchronize(h->stream);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  *done = (rc == 0);
+  return rc;
+}
 int download_rows(hb_handle* h, const float* src, int cols, int ld, double* out) {
+  static const bool mt = getenv("HB_DOWNLOAD_MT") != nullptr;
+  if (mt) {
+    bool done = false;
+    TRY(download_rows_mt(h, src, cols, ld, out, &done));
+    if (done) return 0;
+  }
   const int64_t n = h->n;
   const int64_t rows_per = std::max<int64_t>(1, (int64_t)(h->stage.n / (size_t)cols));
   for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
@@ -1967,6 +2117,14 @@ uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse) {
   while ((1ull << bits) < n) bits++;
   const int half_bits = (bits + 1) / 2;
   return inverse ? hb_permute_inv(i, n, half_bits, key) : hb_permute(i, n, half_bits, key);
+}
+
+// Host worker pool (test hook, host only): out[i] = (double) in[i] with `threads` threads (first call fixes the
+// pool size for the process).  Returns the number of threads of the pool.
+int hb_debug_widen(double* out, const float* in, int64_t n, int threads) {
+  WidenPool* p = widen_pool(threads);
+  if (n > 0) p->widen(out, in, (size_t)n);
+  return p->threads();
 }
 
 // Geometry chooser of the experimental update kernel (test hook, host only).

@@ -44,6 +44,17 @@ __global__ void k_download_rows(const float* __restrict__ src, double* __restric
     out[idx] = (double)src[(int64_t)src_row[r0 + r] * ld + c];
   }
 }
+// float variant for the threaded download path (the host workers widen to double while they scatter)
+__global__ void k_download_rows_f(const float* __restrict__ src, float* __restrict__ out, const int* __restrict__ src_row,
+                                  int64_t r0, int64_t rows, int cols, int ld) {
+  int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / cols;
+    int c = (int)(idx - r * cols);
+    out[idx] = src[(int64_t)src_row[r0 + r] * ld + c];
+  }
+}
 __global__ void k_fill_f(float* __restrict__ out, int64_t n, float v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
 }

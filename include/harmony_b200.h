@@ -144,6 +144,9 @@ int hb_enable_timing(hb_handle* h, int on);
  * (inverse = 1) in the keyed pseudo-random order of n cells that replaces arma::shuffle (harmony.cpp:272-273)
  * when no update order is injected.  Returns ~0 for i >= n. */
 uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse);
+/* Test hook (host only): the host worker pool of the threaded download path (HB_DOWNLOAD_MT=1) widens n floats to
+ * doubles; `threads` sizes the pool on first use (<= 0: HB_HOST_THREADS or the core count).  Returns the pool size. */
+int hb_debug_widen(double* out, const float* in, int64_t n, int threads);
 /* Test hook (host only): lane / stage geometry the experimental update kernel (HB_UPDATE_V3=1) would use for
  * rows of KS floats and nb blocks: out = {NV, LPR, RPI, IT, SR, KP, DU, DL, shared-memory bytes}.  Returns 1 if
  * the shape is supported, 0 if the library would fall back to the default kernel. */

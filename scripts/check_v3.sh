@@ -15,12 +15,15 @@ for sw in HB_APPLY_V2 HB_STATS_V2; do   # the deeper-ring variants of the ridge 
   env $sw=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_$sw.json
 done
 HB_UPDATE_V3=1 HB_TRACE_STEPS=0 timeout 300 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null
+# end-to-end: where do the one-off milliseconds go, and does the threaded download help?
+HB_TRACE_HOST=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e_trace.json 2> gpurun_out/host_trace.txt
+HB_DOWNLOAD_MT=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e_mt.json
 python - <<'PY'
 import json
-for n in ("default", "v3", "HB_APPLY_V2", "HB_STATS_V2"):
+for n in ("default", "v3", "HB_APPLY_V2", "HB_STATS_V2", "e2e_trace", "e2e_mt"):
     try:
         d = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
-        print(n, d["ms_per_step"], d.get("regions_ms_per_step"))
+        print(n, d["ms_per_step"], (d.get("e2e") or {}).get("seconds"), d.get("regions_ms_per_step"))
     except Exception as e:
         print(n, "failed:", e)
 PY

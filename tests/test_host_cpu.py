@@ -170,3 +170,19 @@ def test_update_v3_geometry_covers_every_row_width(nb):
     if nb <= 20:
         assert L.hb_debug_update_geometry(100, nb, out) and list(out)[:3] == [5, 5, 6]   # K = 100: 5 lanes x 5 float4
         assert supported >= 100
+
+
+def test_host_widen_pool_matches_numpy():
+    """The worker pool of the threaded download path (HB_DOWNLOAD_MT=1) widens float32 to float64 exactly, for
+    sizes around its slice boundaries and repeatedly (the pool is persistent)."""
+    import ctypes
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    nthreads = None
+    for n in [0, 1, 7, (1 << 18) - 1, 1 << 18, (1 << 18) + 1, 3 * (1 << 18) + 12345, 5_000_000]:
+        src = rng.standard_normal(n).astype(np.float32)
+        out = np.full(n, np.nan)
+        t = L.hb_debug_widen(out.ctypes.data_as(ctypes.c_void_p), src.ctypes.data_as(ctypes.c_void_p), n, 4)
+        nthreads = nthreads or t
+        assert t == nthreads and t >= 1
+        assert np.array_equal(out, src.astype(np.float64))
