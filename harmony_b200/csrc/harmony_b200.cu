@@ -30,6 +30,7 @@
 #include "update_kernel.cuh"
 #include "update_kernel3.cuh"
 #include "assign_tc.cuh"
+#include "assign_tc2.cuh"
 #include "apply_tc.cuh"
 #include "apply_tc2.cuh"
 #include "stats_tc.cuh"
@@ -472,10 +473,17 @@ int run_assign(hb_handle* h, bool normalise) {
       CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 64 * 24, h->stream));
       t.dbg = h->dbg.p;
     }
-    const size_t smem_tc = assign_tc_smem_bytes(t.KD, t.NP, KS);
-    CK(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
     const int grid_tc = std::max(1, std::min(h->tc_ntiles, h->num_sms));
-    k_assign_tc<<<grid_tc, TC_THREADS, smem_tc, h->stream>>>(t);
+    static const bool assign_v2 = getenv("HB_ASSIGN_V2") != nullptr;  // experimental rewrite (assign_tc2.cuh)
+    if (assign_v2 && !tracing && t.NP <= 128 && assign_tc2_smem_bytes(t.KD, t.NP, h->DS) <= 227 * 1024) {
+      const size_t smem_tc = assign_tc2_smem_bytes(t.KD, t.NP, h->DS);
+      CK(cudaFuncSetAttribute(k_assign_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      k_assign_tc2<<<grid_tc, A2_THREADS, smem_tc, h->stream>>>(t);
+    } else {
+      const size_t smem_tc = assign_tc_smem_bytes(t.KD, t.NP, KS);
+      CK(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      k_assign_tc<<<grid_tc, TC_THREADS, smem_tc, h->stream>>>(t);
+    }
     CKL();
     if (tracing) {
       std::vector<long long> st(64 * 24);

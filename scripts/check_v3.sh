@@ -9,7 +9,7 @@ HB_UPDATE_V3=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_
 echo "parity exit: $?"
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json
 HB_UPDATE_V3=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_v3.json
-for sw in HB_APPLY_V2 HB_STATS_V2; do   # the deeper-ring variants of the ridge kernels, one at a time
+for sw in HB_APPLY_V2 HB_STATS_V2 HB_ASSIGN_V2; do   # the other experimental kernels, one at a time
   env $sw=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_run or stepwise"
   echo "$sw parity exit: $?"
   env $sw=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_$sw.json
@@ -20,7 +20,7 @@ HB_TRACE_HOST=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseli
 HB_DOWNLOAD_MT=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e_mt.json
 python - <<'PY'
 import json
-for n in ("default", "v3", "HB_APPLY_V2", "HB_STATS_V2", "e2e_trace", "e2e_mt"):
+for n in ("default", "v3", "HB_APPLY_V2", "HB_STATS_V2", "HB_ASSIGN_V2", "e2e_trace", "e2e_mt"):
     try:
         d = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
         print(n, d["ms_per_step"], (d.get("e2e") or {}).get("seconds"), d.get("regions_ms_per_step"))
