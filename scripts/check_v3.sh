@@ -5,12 +5,17 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-HB_UPDATE_V3=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_runharmony.py -x -q -m gpu
+# a hang costs its whole timeout in GPU minutes: smoke every switch first with a short leash
+for sw in HB_UPDATE_V3 HB_APPLY_V2 HB_STATS_V2 HB_ASSIGN_V2 HB_DOWNLOAD_MT; do
+  env $sw=1 timeout 120 python -c "import __graft_entry__ as g; g.smoke()"
+  echo "$sw smoke exit: $?"
+done
+HB_UPDATE_V3=1 timeout 420 python -m pytest tests/test_gpu_parity.py tests/test_gpu_runharmony.py -x -q -m gpu
 echo "parity exit: $?"
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json
 HB_UPDATE_V3=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_v3.json
 for sw in HB_APPLY_V2 HB_STATS_V2 HB_ASSIGN_V2; do   # the other experimental kernels, one at a time
-  env $sw=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_run or stepwise"
+  env $sw=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full_run or stepwise"
   echo "$sw parity exit: $?"
   env $sw=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_$sw.json
 done
