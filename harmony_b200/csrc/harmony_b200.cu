@@ -896,6 +896,8 @@ int upd3_launch(hb_handle* h, const UpdArgs& a, bool cooperative) {
   p.a.use_barrier = cooperative ? 1 : 0;
   p.g = h->g3;
   if (h->use_xch) p.x = h->xch;
+  static const bool no_hints = getenv("HB_V3_NO_L2_HINTS") != nullptr;
+  p.l2_hints = no_hints ? 0 : 1;
   switch (h->g3.NV) {
     case 1: return upd3_launch_nv<1>(h, p, cooperative);
     case 2: return upd3_launch_nv<2>(h, p, cooperative);

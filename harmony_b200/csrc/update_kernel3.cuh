@@ -62,6 +62,8 @@ struct Upd3Args {
   UpdArgs a;
   Upd3Geom g;
   Upd3Xch x;
+  int l2_hints = 1;  // look-ahead rows are loaded evict_last (the update group re-reads them a few steps later),
+                     // the update group's own loads evict_first (last use of the row in this round)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
@@ -266,6 +268,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
     const int s0 = forU ? a.s_begin : look_first;
     const int s1 = forU ? a.s_end - 1 : look_last;
     int slot = 0, use = 0;  // stage g lives in slot g % D; use = g / D
+    const uint64_t policy = forU ? umma::l2_policy_evict_first() : umma::l2_policy_evict_last();
     for (int s = s0; s <= s1; ++s) {
       int lo, hi, q;
       range_of(s, lo, hi, q);
@@ -285,7 +288,13 @@ __global__ void __launch_bounds__(U3_THREADS, 1) k_update_steps3(Upd3Args p) {
         __syncwarp();
         if (lane == 0) umma::mbar_arrive_expect_tx(full + slot, (uint32_t)nr * row_bytes);
         __syncwarp();
-        if (valid) umma::bulk_load(ring + ((size_t)slot * SR + lane) * KP, src + (size_t)cell * KS, row_bytes, full + slot);
+        if (valid) {
+          float* dstp = ring + ((size_t)slot * SR + lane) * KP;
+          if (p.l2_hints)
+            umma::bulk_load_hint(dstp, src + (size_t)cell * KS, row_bytes, full + slot, policy);
+          else
+            umma::bulk_load(dstp, src + (size_t)cell * KS, row_bytes, full + slot);
+        }
         if (++slot == D) {
           slot = 0;
           ++use;
