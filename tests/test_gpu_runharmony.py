@@ -134,3 +134,26 @@ def test_properties_at_full_size():
     assert len(ok) == 1 + 2 * 4 and np.all(np.isfinite(ok))
     # idempotence of the read path and un-sorting: getZorig returns the input (fp32-rounded), in input order
     np.testing.assert_array_equal(g.getZorig().T[:1000], Z[:1000].astype(np.float32))
+
+
+def test_library_reproduces_the_tables_printed_by_the_reference_vignette():
+    """Same golden values as tests/test_oracle.py (doc/detailedWalkthrough.html:656-708 of the reference), through
+    the C ABI: init_cluster_cpp with the matching centroids must leave round(O), round(E) equal to the 30 integers
+    the reference printed (the closest value to a rounding boundary, 398.52, is 0.02 away — 20x the fp32 error)."""
+    import os
+    from harmony_b200 import prepare_inputs
+    from harmony_b200.harmony import harmony
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "vignette_walkthrough.npz"))
+    Z, meta = load_cell_lines(small=False)
+    a = prepare_inputs(Z, meta, "dataset", nclust=5, theta=1.0)
+    h = harmony(device=0)
+    h.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], a["max_iter_kmeans"],
+            a["epsilon_kmeans"], a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"],
+            a["batch_proportion_cutoff"], False)
+    h.init_cluster_cpp(g["Y"])
+    assert np.array_equal(np.round(np.asarray(h.O)), g["O_init"])
+    assert np.array_equal(np.round(np.asarray(h.E)), g["E_init"])
+    R = np.asarray(h.R)                      # K x N like harmonyObj$R
+    ct = np.stack([(meta["cell_type"] == lv) for lv in ("jurkat", "t293")], axis=1).astype(np.float64)
+    assert np.abs(np.round(R @ ct) - g["celltype_init"]).max() <= 1
