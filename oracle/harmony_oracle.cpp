@@ -4,20 +4,25 @@
 // it is the checker for tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs.
 //
-// PARITY STATUS: pinned for the assignment step, *parity unpinned* for update_R and the ridge
-// correction.  The reference (immunogenomics/harmony @ df19af23, v2.0.4) ships no known-answer
-// tests for this path (tests/testthat/*.R pin invariants only) and cannot be built here (needs R,
-// Rcpp and an un-vendored, un-pinned RcppArmadillo).  The one set of numbers the reference itself
-// printed is in its rendered vignette: doc/detailedWalkthrough.html:656-708 shows round(O),
-// round(E) and the cluster x cell-type counts left by init_cluster_cpp on data(cell_lines) with
-// nclust = 5.  tests/golden/make_vignette_fixture.py recovers the matching k-means centroids and
-// tests/test_oracle.py checks that this restatement reproduces all 30 integers of O and E from
-// them (the library is held to the same in tests/test_gpu_runharmony.py).  Everything after the
-// first update_R call depends on R's random stream and on a centroid step the mounted version no
-// longer runs (the vignette was rendered before it was commented out, harmony.cpp:236-238), so
-// the rest of the path follows the reference operation by operation (citations below), is checked
-// against the reference's own test invariants on the reference's own fixtures
-// (tests/test_oracle.py) and against an independent numpy restatement of the plain-R formulas in
+// PARITY STATUS: pinned against numbers the reference itself printed for the assignment step and
+// for cluster_cpp (update_R, compute_objective, convergence window); *parity unpinned* for the
+// ridge correction.  The reference (immunogenomics/harmony @ df19af23, v2.0.4) ships no
+// known-answer tests for this path (tests/testthat/*.R pin invariants only) and cannot be built
+// here (needs R, Rcpp and an un-vendored, un-pinned RcppArmadillo).  Its rendered vignette,
+// doc/detailedWalkthrough.html, does print tables of a run on data(cell_lines) with nclust = 5:
+//   :656-708  round(O), round(E), cluster x cell-type counts after init_cluster_cpp
+//   :733-786  round(O), cell-type counts and error rates after max_iter_kmeans <- 10; cluster_cpp()
+//   :844-850  round((E / O)^theta, 2) of that state
+// tests/golden/make_vignette_fixture.py recovers the k-means centroids that reproduce the first
+// set (R's random stream cannot be replayed), and tests/test_oracle.py checks that this
+// restatement (fp32 and fp64) and the numpy restatement reproduce all 55 printed integers exactly
+// and the 15 ratios to 3 % — for cluster_cpp with `legacy_centroid_step` on: the vignette was
+// rendered while STEP 1 of harmony.cpp:235-238 (commented out in the mounted 2.0.4) still ran,
+// and the tables come out right only with it, for any update order, and only if the convergence
+// window stops the loop after 5 rounds.  moe_correct_ridge_cpp has no printed output anywhere in
+// the reference; for it this file follows the reference operation by operation (citations below)
+// and is checked against the reference's own test invariants on the reference's own fixtures and
+// against an independent numpy restatement of the plain-R formulas of
 // vignettes/detailedWalkthrough.Rmd (tests/numpy_restatement.py).
 //
 // What is restated (all citations into /root/reference/):
@@ -156,6 +161,7 @@ struct Harmony : Base {
       objective_harmony;
   float block_size = 0, epsilon_kmeans = 0, epsilon_harmony = 0, alpha = 0, batch_proportion_cutoff = 0;
   unsigned max_iter_kmeans = 0, window_size = 3;
+  bool legacy_centroid_step = false;  // harmony.cpp:235-238 (see cluster())
   bool lambda_estimation = false, ran_setup = false, ran_init = false;
   int W_rows = 0;
   int warn_small = 0;
@@ -344,6 +350,20 @@ struct Harmony : Base {
       assign_from_centroids();
     }
     for (iter = 0; iter < max_iter_kmeans; iter++) {
+      if (legacy_centroid_step) {
+        // STEP 1 of harmony.cpp:235-238 — commented out in the mounted 2.0.4, still run by the package
+        // version that rendered doc/detailedWalkthrough.html (whose printed tables are golden values):
+        //   Y = arma::normalise(Z_corr * R.t(), 2, 0);  dist_mat = 2 * (1 - Y.t() * Z_corr);
+        std::fill(Y.begin(), Y.end(), T(0));
+        for (int64_t i = 0; i < N; ++i)
+          for (int k = 0; k < K; ++k) {
+            const T r = R[i * K + k];
+            for (int c = 0; c < d; ++c) Y[(size_t)k * d + c] += Z_corr[i * d + c] * r;
+          }
+        normalise_cols_l2(Y.data(), d, K);
+        gemm_tn<T>(K, N, d, Y.data(), Z_corr.data(), dist_mat.data());
+        for (size_t i = 0; i < dist_mat.size(); ++i) dist_mat[i] = T(2) * (T(1) - dist_mat[i]);
+      }
       int st = update_R(perms + (size_t)iter * N);
       if (st != 0) return st;
       compute_objective();
@@ -721,6 +741,14 @@ int ho_moe_correct_ridge(void* hv) { return DISPATCH((Handle*)hv, moe_correct_ri
 int ho_check_convergence(void* hv, int type) { return DISPATCH((Handle*)hv, check_convergence(type)); }
 void ho_compute_objective(void* hv) { DISPATCH((Handle*)hv, compute_objective()); }
 int ho_warned_small(void* hv) { return DISPATCH((Handle*)hv, warn_small); }
+int ho_set_legacy_centroid_step(void* hv, int on) {
+  Handle* h = (Handle*)hv;
+  if (h->use_double)
+    h->dd->legacy_centroid_step = on != 0;
+  else
+    h->f->legacy_centroid_step = on != 0;
+  return 0;
+}
 int ho_set_max_iter_kmeans(void* hv, int v) {
   Handle* h = (Handle*)hv;
   if (h->use_double)

@@ -51,6 +51,7 @@ def lib():
         L.ho_compute_objective.argtypes = [P]
         L.ho_warned_small.argtypes = [P]
         L.ho_set_max_iter_kmeans.argtypes = [P, ctypes.c_int]
+        L.ho_set_legacy_centroid_step.argtypes = [P, ctypes.c_int]
         L.ho_get.argtypes = [P, ctypes.c_int, P]
         L.ho_trace.restype = ctypes.c_int64
         L.ho_trace.argtypes = [P, ctypes.c_int, P, ctypes.c_int64]
@@ -145,6 +146,10 @@ class OracleHarmony:
 
     def compute_objective(self):
         self.L.ho_compute_objective(self.h)
+
+    def set_legacy_centroid_step(self, on=True):
+        """Run STEP 1 of harmony.cpp:235-238 (centroid update, commented out in 2.0.4) in every clustering round."""
+        self.L.ho_set_legacy_centroid_step(self.h, int(bool(on)))
 
     def set_max_iter_kmeans(self, v):
         self.L.ho_set_max_iter_kmeans(self.h, int(v))

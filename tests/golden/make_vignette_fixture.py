@@ -7,13 +7,19 @@ harmony::init_cluster_cpp (src/harmony.cpp:131-156) on data/cell_lines.RData:
     detailedWalkthrough.html:677-682              round(harmonyObj$E)
     detailedWalkthrough.html:703-708              round(R %*% t(phi_celltype))
 
+After `harmonyObj$max_iter_kmeans <- 10; harmonyObj$cluster_cpp()` the vignette prints the same tables again
+(:733-739 round(O), :769-775 cell types, :786 the per-cluster error rates): the state left by cluster_cpp
+(src/harmony.cpp:208-262: update_R, compute_objective and the convergence window) — rendered with a package
+version that still ran the centroid update at the top of every round (STEP 1, harmony.cpp:235-238, commented out in
+the mounted 2.0.4).  With that step switched on the restatements reproduce these 25 integers exactly, for every
+update order tried (the tables do not depend on the shuffle at this resolution), and only if the convergence
+window stops the loop after 5 rounds as the reference does.
+
 The centroids came from R's RNG (set.seed(1) + arma::kmeans) and cannot be replayed here, but the tables can: this
 script runs Lloyd iterations from random subsets of the cosine-normalised cells (numpy, seeded) until it finds the
 k-means solution for which the assignment-step formulas reproduce all 30 printed integers of O and E, and stores
 those centroids next to the printed tables in tests/golden/vignette_walkthrough.npz.  The oracle (and the library)
-must then reproduce the tables from the centroids.  The later tables of the vignette (after cluster_cpp) were
-rendered with a package version that still had the centroid update inside the clustering loop
-(src/harmony.cpp:236-238, commented out in the mounted 2.0.4) and are not used.
+must then reproduce the tables from the centroids.
 
 Run from the repo root:  python tests/golden/make_vignette_fixture.py"""
 import itertools
@@ -27,6 +33,12 @@ O_INIT = np.array([[158, 0, 295], [3, 419, 0], [8, 399, 0], [248, 0, 405], [429,
 E_INIT = np.array([[162, 158, 134], [151, 147, 125], [145, 141, 120], [233, 227, 193], [155, 151, 129]], dtype=np.float64)
 CELLTYPE_INIT = np.array([[2, 452], [422, 0], [406, 0], [0, 652], [435, 0]], dtype=np.float64)  # jurkat, t293
 SIGMA = 0.1  # RunHarmony default
+O_CLUSTERED = np.array([[176, 0, 324], [7, 401, 0], [13, 408, 0], [230, 0, 376], [420, 15, 0]], dtype=np.float64)
+CELLTYPE_CLUSTERED = np.array([[2, 498], [408, 0], [421, 0], [0, 606], [435, 0]], dtype=np.float64)
+ERROR_RATE_CLUSTERED = np.array([0.425, 0.000, 0.000, 0.019, 0.000])  # round(min row proportion * 100, 3)
+# round((E / O)^1, 2) of the same state (:844-850): spans nine orders of magnitude (the tails of exp(-dist / sigma))
+E_OVER_O_CLUSTERED = np.array([[1.01, 2702150.70, 0.46], [20.88, 0.35, 353142040.63], [11.58, 0.36, 12842105.70],
+                               [0.94, 1109875.94, 0.48], [0.37, 10.06, 938593575.72]])
 
 
 def soft_tables(Zn, Y, Phi, Pr_b):
@@ -62,7 +74,9 @@ def main():
             if np.array_equal(np.round(O[p]), O_INIT) and np.array_equal(np.round(E[p]), E_INIT):
                 out = os.path.join(HERE, "vignette_walkthrough.npz")
                 np.savez(out, Y=Y[p].astype(np.float64), O_init=O_INIT, E_init=E_INIT, celltype_init=CELLTYPE_INIT,
-                         sigma=SIGMA, trial=trial)
+                         O_clustered=O_CLUSTERED, celltype_clustered=CELLTYPE_CLUSTERED,
+                         error_rate_clustered=ERROR_RATE_CLUSTERED, e_over_o_clustered=E_OVER_O_CLUSTERED, sigma=SIGMA,
+                         trial=trial)
                 print(f"trial {trial}: all 30 integers of O and E reproduced -> {out}")
                 return
     raise SystemExit("no k-means solution reproduces the printed tables")

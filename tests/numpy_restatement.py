@@ -94,13 +94,24 @@ class NumpyHarmony:
             self.E += np.outer(Rn.sum(axis=0), self.Pr_b)
             self.O += Rn.T @ Pb.T
 
+    legacy_centroid_step = False   # STEP 1 of harmony.cpp:235-238, commented out in 2.0.4
+    window_size, epsilon_kmeans = 3, 1e-3
+
     def cluster(self, perms):
         if len(self.obj_harmony) != 1:
             self.Z_corr = self._l2(self.Z_corr)
             self._assign()
         for t in range(self.T):
+            if self.legacy_centroid_step:
+                self.Y = self._l2(self.R.T @ self.Z_corr)
+                self.D = 2.0 * (1.0 - self.Z_corr @ self.Y.T)
             self.update_R(perms[t])
             self.compute_objective()
+            if t > self.window_size:                                   # harmony.cpp:249-256 + :176-189
+                o, w = self.obj_kmeans, self.window_size
+                old, new = sum(o[-2 - i] for i in range(w)), sum(o[-1 - i] for i in range(w))
+                if abs(old - new) / abs(old) < self.epsilon_kmeans:
+                    break
         self.obj_harmony.append(self.obj_kmeans[-1])
 
     def moe_correct_ridge(self):

@@ -228,3 +228,54 @@ def test_oracle_reproduces_the_tables_printed_by_the_reference_vignette(double):
     R = R if R.shape[0] == Z.shape[0] else R.T
     ct = np.stack([(meta["cell_type"] == lv) for lv in ("jurkat", "t293")], axis=1).astype(np.float64)
     assert np.abs(np.round(R.T @ ct) - g["celltype_init"]).max() <= 1
+
+
+def _vignette_clustered_state(impl, double, seed):
+    """init_cluster_cpp from the vignette's centroids, max_iter_kmeans <- 10, cluster_cpp() with the centroid step
+    of harmony.cpp:235-238 switched on.  Returns O (K x B), R (N x K), number of rounds."""
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "vignette_walkthrough.npz"))
+    Z, meta = load_cell_lines(small=False)
+    a = prepare_inputs(Z, meta, "dataset", nclust=5, theta=1.0)
+    perms = make_perms(Z.shape[0], 10, seed)
+    if impl == "numpy":
+        h = NumpyHarmony(a["Z"], a["phi_i"], a["B_vec"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], 10, a["K"],
+                         a["block_size"], a["batch_proportion_cutoff"])
+        h.legacy_centroid_step = True
+        h.init_cluster(g["Y"])
+        h.cluster(perms)
+        return g, meta, h.O, h.R, len(h.obj_kmeans) - 1
+    from oracle.oracle import OracleHarmony
+    o = OracleHarmony(double=double)
+    args = setup_args(a)
+    args["max_iter_kmeans"] = 10
+    o.setup(**args)
+    o.set_legacy_centroid_step(True)
+    o.init_cluster_cpp(g["Y"])
+    o.cluster_cpp(perms)
+    R = np.asarray(o.get("R"))
+    return g, meta, np.asarray(o.get("O")).T, (R if R.shape[0] == Z.shape[0] else R.T), int(o.trace("kmeans_rounds")[-1])
+
+
+@pytest.mark.parametrize("impl,double", [("numpy", True), ("oracle", False), ("oracle", True)])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_restatements_reproduce_the_vignette_tables_after_cluster_cpp(impl, double, seed):
+    """Golden values for update_R + compute_objective + the convergence window: after `max_iter_kmeans <- 10;
+    cluster_cpp()` the reference's vignette prints round(O) (doc/detailedWalkthrough.html:733-739), the cluster x
+    cell-type counts (:769-775) and the per-cluster error rates (:786).  It was rendered while STEP 1 of
+    harmony.cpp:235-238 (centroid update) was still active; with that step on, both restatements give exactly the
+    25 printed integers for any update order — and only because the loop stops after 5 rounds like the reference
+    (10 rounds would be off by one)."""
+    g, meta, O, R, rounds = _vignette_clustered_state(impl, double, seed)
+    assert rounds == 5
+    assert np.array_equal(np.round(O), g["O_clustered"])
+    ct = np.stack([(meta["cell_type"] == lv) for lv in ("jurkat", "t293")], axis=1).astype(np.float64)
+    counts = R.T @ ct
+    assert np.array_equal(np.round(counts), g["celltype_clustered"])
+    err = (counts / counts.sum(axis=1, keepdims=True)).min(axis=1) * 100.0
+    assert np.abs(err - g["error_rate_clustered"]).max() < (6e-4 if double else 2e-3)   # printed with 3 decimals
+    # round((E / O)^theta, 2) of the same state (:844-850): 15 values from 0.35 to 9.4e8, i.e. down to the 1e-7
+    # tails of exp(-dist / sigma); they move by ~1 % with the last digits of the centroids, which are not R's
+    E = np.outer(R.sum(axis=0), np.bincount(np.unique(meta["dataset"], return_inverse=True)[1]) / R.shape[0])
+    assert np.abs(E / O / g["e_over_o_clustered"] - 1.0).max() < 0.03
