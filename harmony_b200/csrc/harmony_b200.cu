@@ -287,6 +287,9 @@ struct hb_handle {
   DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
   int tc_ntiles = 0;
   bool use_tc_assign = false, use_tc_apply = false, use_tc_stats = false;
+  bool legacy_centroid = false;  // HB_LEGACY_CENTROID_STEP: centroid update at the top of every clustering round
+  DevBuf<float> Rkeep, OEkeep;   // R / O,E saved around the distance-only assignment of that step
+  DevBuf<double> objkeep;
   bool use_v3 = false;  // experimental second-generation update kernel (HB_UPDATE_V3=1)
   Upd3Geom g3{};
   bool use_xch = false;  // v3 + sharded cells: block steps exchanged through peer memory (HB_PEER_EXCHANGE=1)
@@ -1801,6 +1804,78 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
   return 0;
 }
 
+// STEP 1 of harmony::cluster_cpp as it ran before 2.0.4 (harmony.cpp:235-238):
+//   Y = arma::normalise(Z_corr * R.t(), 2, 0);   dist_mat = 2 * (1 - Y.t() * Z_corr);
+// built from the kernels of the ridge statistics (R^T [Z_corr | 1] per tuple) and of the assignment.  The
+// assignment kernels also rewrite R, O, E and the objective sums, which this step must leave alone: they are
+// saved and restored around the call (compatibility path, not a fast one).
+int legacy_centroid_step(hb_handle* h) {
+  const int K = h->K, d = h->d, B = h->B, J = h->J, KS = h->KS;
+  const int D1 = d + 1;
+  const size_t nK = (size_t)h->n * KS, BK = (size_t)B * KS;
+  CK(cudaMemsetAsync(h->S.p, 0, sizeof(float) * (size_t)J * K * D1, h->stream));
+  if (h->use_tc_stats) {
+    StatsTcArgs t;
+    t.R = h->R.p;
+    t.Zo = h->Zc.p;  // the statistics of the corrected, normalised embedding
+    t.tile_cell0 = h->tile_cell0.p;
+    t.tile_len = h->tile_len.p;
+    t.tile_tuple = h->tile_tuple.p;
+    t.S = h->S.p;
+    t.ntiles = h->ntiles;
+    t.d = d;
+    t.K = K;
+    t.KS = KS;
+    t.DS = h->DS;
+    t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
+    const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
+    const size_t smem_tc = stats_tc_smem_bytes(KS, h->DS);
+    CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+    k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+    CKL();
+  } else {
+    StatsArgs a;
+    a.R = h->R.p;
+    a.Zo = h->Zc.p;
+    a.tile_cell0 = h->tile_cell0.p;
+    a.tile_len = h->tile_len.p;
+    a.tile_tuple = h->tile_tuple.p;
+    a.S = h->S.p;
+    a.ntiles = h->ntiles;
+    a.d = d;
+    a.K = K;
+    a.KS = (K <= 128) ? K : 128;
+    a.ldR = KS;
+    a.ldZ = h->DS;
+    const int KSP = (a.KS + 7) & ~7, DP = (D1 + 3) & ~3;
+    dim3 block(DP / 4, KSP / 8);
+    if (block.x * block.y > 1024) return fail(h, 2, "d = %d is too large for the statistics kernel", d);
+    a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms * 4 - 1) / (h->num_sms * 4));
+    dim3 grid((h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta, (K + a.KS - 1) / a.KS);
+    size_t smem = sizeof(float) * (size_t)TM * (KSP + DP);
+    CK(cudaFuncSetAttribute(k_ridge_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ridge_stats<<<grid, block, smem, h->stream>>>(a);
+    CKL();
+  }
+  TRY(allreduce_f(h, h->S.p, (size_t)J * K * D1));
+  k_centroids_from_stats<<<K, 64, sizeof(float) * (size_t)d, h->stream>>>(h->S.p, h->Y.p, J, K, d);
+  CKL();
+  // distances to the new centroids -> U; everything else the assignment writes is put back
+  if (h->Rkeep.n < nK) CK(h->Rkeep.alloc(nK));
+  if (h->OEkeep.n < 2 * BK) CK(h->OEkeep.alloc(2 * BK));
+  if (h->objkeep.n < 2) CK(h->objkeep.alloc(2));
+  CK(cudaMemcpyAsync(h->Rkeep.p, h->R.p, sizeof(float) * nK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->OEkeep.p, h->O.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->OEkeep.p + BK, h->E.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->objkeep.p, h->obj_acc.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  TRY(run_assign(h, false));
+  CK(cudaMemcpyAsync(h->R.p, h->Rkeep.p, sizeof(float) * nK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->O.p, h->OEkeep.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->E.p, h->OEkeep.p + BK, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->obj_acc.p, h->objkeep.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
 int ensure_plan_rounds(hb_handle* h, int T) {
   if (T <= h->plan_rounds) return 0;
   if (h->plan_stream) CK(cudaStreamSynchronize(h->plan_stream));
@@ -1843,7 +1918,29 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
   }
   if (h->abort_cb && h->abort_cb(h->abort_user)) return -1;  // Progress::check_abort (:233)
   unsigned iter = 0;
-  if (h->use_v2) {
+  if (h->legacy_centroid) {
+    // compatibility path: centroid step + one first-generation update_R per round
+    if (h->next_ready) {  // a plan prebuilt by an earlier call on the side stream is not used here
+      CK(cudaStreamWaitEvent(h->stream, h->plan_done, 0));
+      h->round_counter -= (uint64_t)h->next_T;
+      h->next_ready = false;
+    }
+    for (iter = 0; iter < T; iter++) {
+      if (iter > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
+      TRY(legacy_centroid_step(h));  // :235-238
+      TRY(build_plan(h, 0, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr, 0, h->stream));
+      TRY(run_update_R_v1(h, 0));  // :241
+      TRY(push_objective(h));      // :248
+      if (iter > h->window_size) {  // :250-256
+        int conv = 0;
+        TRY(check_convergence_host(h, 0, &conv));
+        if (conv) {
+          iter++;
+          break;
+        }
+      }
+    }
+  } else if (h->use_v2) {
     // all T update orders are drawn up front (they do not depend on the data), then the rounds run in
     // chunks: [0, window_size + 2) in one launch, afterwards one round per launch (convergence checks)
     // The native orders of a call depend only on (seed, round counter), so the plan of the NEXT call is
@@ -1895,7 +1992,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
       }
     }
   }
-  if (h->use_v2 && !update_orders && T > 0 && !h->timing && getenv("HB_NO_PLAN_OVERLAP") == nullptr) {
+  if (h->use_v2 && !h->legacy_centroid && !update_orders && T > 0 && !h->timing && getenv("HB_NO_PLAN_OVERLAP") == nullptr) {
     // prebuild the next call's plan into the other buffer set on the side stream; it starts once this
     // call's own (main-stream) plan build and update kernel are done with the shared scan scratch
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -2053,6 +2150,7 @@ int hb_get_scalar(const hb_handle* h, int which, double* out) {
     case HB_EPSILON_HARMONY: *out = h->epsilon_harmony; return 0;
     case HB_LAMBDA_ESTIMATION: *out = h->lambda_estimation ? 1 : 0; return 0;
     case HB_WINDOW_SIZE: *out = h->window_size; return 0;
+    case HB_LEGACY_CENTROID_STEP: *out = h->legacy_centroid ? 1 : 0; return 0;
   }
   return 2;
 }
@@ -2067,6 +2165,7 @@ int hb_set_scalar(hb_handle* h, int which, double value) {
       return 0;
     case HB_EPSILON_KMEANS: h->epsilon_kmeans = (float)value; return 0;
     case HB_EPSILON_HARMONY: h->epsilon_harmony = (float)value; return 0;
+    case HB_LEGACY_CENTROID_STEP: h->legacy_centroid = value != 0.0; return 0;
   }
   return fail(h, 2, "scalar %d is not writable", which);
 }

@@ -44,6 +44,23 @@ __global__ void k_download_rows(const float* __restrict__ src, double* __restric
     out[idx] = (double)src[(int64_t)src_row[r0 + r] * ld + c];
   }
 }
+// Legacy centroid step (harmony.cpp:235-238, commented out in 2.0.4): Y_k = normalise(sum_i R_ik z_i) from the
+// per-tuple sums S[q][k][0..d) of the statistics kernels run on Z_corr.  One block per cluster.
+__global__ void k_centroids_from_stats(const float* __restrict__ S, float* __restrict__ Y, int J, int K, int d) {
+  extern __shared__ float ysum[];  // [d]
+  const int k = blockIdx.x, D1 = d + 1;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < J; ++q) t += S[((size_t)q * K + k) * D1 + c];
+    ysum[c] = t;
+  }
+  __syncthreads();
+  float ss = 0.f;
+  for (int c = 0; c < d; ++c) ss += ysum[c] * ysum[c];  // every thread: d is small
+  float nrm = sqrtf(ss);
+  if (nrm == 0.f) nrm = 1.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) Y[(size_t)k * d + c] = ysum[c] / nrm;
+}
 // float variant for the threaded download path (the host workers widen to double while they scatter)
 __global__ void k_download_rows_f(const float* __restrict__ src, float* __restrict__ out, const int* __restrict__ src_row,
                                   int64_t r0, int64_t rows, int cols, int ld) {

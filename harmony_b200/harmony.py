@@ -17,10 +17,11 @@ from . import _lib
 FIELD = {"Z_corr": 0, "Z_orig": 1, "R": 2, "Y": 3, "O": 4, "E": 5, "W": 6, "Pr_b": 7, "theta": 8, "sigma": 9,
          "lambda_mat": 10, "lambda": 11}
 SCALAR = {"N": 0, "B": 1, "K": 2, "d": 3, "C": 4, "alpha": 5, "max_iter_kmeans": 6, "block_size": 7,
-          "epsilon_kmeans": 8, "epsilon_harmony": 9, "N_local": 10, "lambda_estimation": 11, "window_size": 12}
+          "epsilon_kmeans": 8, "epsilon_harmony": 9, "N_local": 10, "lambda_estimation": 11, "window_size": 12,
+          "legacy_centroid_step": 13}
 TRACE = {"objective_kmeans": 0, "objective_kmeans_dist": 1, "objective_kmeans_entropy": 2,
          "objective_kmeans_cross": 3, "objective_harmony": 4, "kmeans_rounds": 5}
-_INT_SCALARS = ("N", "B", "K", "d", "C", "max_iter_kmeans", "N_local", "window_size")
+_INT_SCALARS = ("N", "B", "K", "d", "C", "max_iter_kmeans", "N_local", "window_size", "legacy_centroid_step")
 
 
 def _ptr(a):
@@ -186,7 +187,7 @@ class harmony:
     def __getattr__(self, name):
         if name.startswith("_"):
             raise AttributeError(name)
-        if name in ("N", "B", "K", "d", "alpha", "max_iter_kmeans"):
+        if name in ("N", "B", "K", "d", "alpha", "max_iter_kmeans", "legacy_centroid_step"):
             return self._scalar(name)
         if name == "R":
             return self.getR()
@@ -219,7 +220,7 @@ class harmony:
         if name.startswith("_"):
             object.__setattr__(self, name, value)
             return
-        if name in ("alpha", "max_iter_kmeans"):
+        if name in ("alpha", "max_iter_kmeans", "legacy_centroid_step"):
             self._check(self._L.hb_set_scalar(self._h, SCALAR[name], float(value)))
             return
         shapes = {"Y": ("Y", "d", "K"), "R": ("R", "K", "N_local"), "O": ("O", "K", "B"), "E": ("E", "K", "B")}

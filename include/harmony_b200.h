@@ -116,9 +116,13 @@ int hb_set_field(hb_handle* h, int field, const double* in);
 
 enum hb_scalar { HB_N = 0, HB_B = 1, HB_K = 2, HB_D = 3, HB_C = 4, HB_ALPHA = 5, HB_MAX_ITER_KMEANS = 6,
                  HB_BLOCK_SIZE = 7, HB_EPSILON_KMEANS = 8, HB_EPSILON_HARMONY = 9, HB_N_LOCAL = 10,
-                 HB_LAMBDA_ESTIMATION = 11, HB_WINDOW_SIZE = 12 };
+                 HB_LAMBDA_ESTIMATION = 11, HB_WINDOW_SIZE = 12, HB_LEGACY_CENTROID_STEP = 13 };
 int hb_get_scalar(const hb_handle* h, int which, double* out);
-/* Settable: HB_ALPHA, HB_MAX_ITER_KMEANS (vignettes/detailedWalkthrough.Rmd:364), HB_EPSILON_*. */
+/* Settable: HB_ALPHA, HB_MAX_ITER_KMEANS (vignettes/detailedWalkthrough.Rmd:364), HB_EPSILON_*, and
+ * HB_LEGACY_CENTROID_STEP (0/1): run STEP 1 of harmony::cluster_cpp — Y = normalise(Z_corr * R.t()),
+ * dist_mat = 2 (1 - Y.t() Z_corr), harmony.cpp:235-238, commented out in 2.0.4 — at the top of every clustering
+ * round, as the package version that rendered the reference's vignette did.  Compatibility path: one
+ * statistics + assignment pass per round on top of the first-generation update kernels. */
 int hb_set_scalar(hb_handle* h, int which, double value);
 /* B_vec field (harmony.cpp:683): writes C ints. */
 int hb_get_B_vec(const hb_handle* h, int32_t* out);

@@ -20,6 +20,8 @@ for sw in HB_APPLY_V2 HB_STATS_V2 HB_ASSIGN_V2; do   # the other experimental ke
   env $sw=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_$sw.json
 done
 HB_UPDATE_V3=1 HB_TRACE_STEPS=0 timeout 300 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null
+# the golden tables of the reference's vignette through the library (init: default path; after cluster_cpp: legacy step)
+timeout 300 python -m pytest tests/test_gpu_runharmony.py -q -m gpu -k vignette -rxX
 # end-to-end: where do the one-off milliseconds go, and does the threaded download help?
 HB_TRACE_HOST=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e_trace.json 2> gpurun_out/host_trace.txt
 HB_DOWNLOAD_MT=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e_mt.json

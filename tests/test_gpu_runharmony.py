@@ -157,3 +157,34 @@ def test_library_reproduces_the_tables_printed_by_the_reference_vignette():
     R = np.asarray(h.R)                      # K x N like harmonyObj$R
     ct = np.stack([(meta["cell_type"] == lv) for lv in ("jurkat", "t293")], axis=1).astype(np.float64)
     assert np.abs(np.round(R @ ct) - g["celltype_init"]).max() <= 1
+
+
+@pytest.mark.xfail(strict=False, reason="legacy centroid step (HB_LEGACY_CENTROID_STEP) written without a GPU, first run pending")
+@pytest.mark.parametrize("seed", [0, 1])
+def test_library_reproduces_the_vignette_tables_after_cluster_cpp(seed):
+    """The tables the reference's vignette prints after `max_iter_kmeans <- 10; cluster_cpp()`
+    (doc/detailedWalkthrough.html:733-786) through the C ABI, with the centroid step of harmony.cpp:235-238
+    switched on as in the package version that rendered them: 25 integers, exactly, for any update order, after
+    exactly 5 rounds (see tests/test_oracle.py for the same check on the restatements)."""
+    import os
+    from harmony_b200 import prepare_inputs
+    from harmony_b200.harmony import harmony
+    from helpers import GOLDEN, make_perms
+    g = np.load(os.path.join(GOLDEN, "vignette_walkthrough.npz"))
+    Z, meta = load_cell_lines(small=False)
+    a = prepare_inputs(Z, meta, "dataset", nclust=5, theta=1.0)
+    h = harmony(device=0)
+    h.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], 10,
+            a["epsilon_kmeans"], a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"],
+            a["batch_proportion_cutoff"], False)
+    h.legacy_centroid_step = 1
+    assert h.legacy_centroid_step == 1
+    h.init_cluster_cpp(g["Y"])
+    assert h.cluster_cpp(make_perms(Z.shape[0], 10, seed)) == 0
+    assert int(h.kmeans_rounds[-1]) == 5
+    assert np.array_equal(np.round(np.asarray(h.O)), g["O_clustered"])
+    ct = np.stack([(meta["cell_type"] == lv) for lv in ("jurkat", "t293")], axis=1).astype(np.float64)
+    counts = np.asarray(h.R) @ ct
+    assert np.array_equal(np.round(counts), g["celltype_clustered"])
+    err = (counts / counts.sum(axis=1, keepdims=True)).min(axis=1) * 100.0
+    assert np.abs(err - g["error_rate_clustered"]).max() < 2e-3
