@@ -639,7 +639,7 @@ int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, o
                                                         h->ranges.p + (R0 + t) * nb * h->coop_grid);
     CKL();
   }
-  if (!h->use_v2) {
+  if (!h->use_v2 || h->legacy_centroid) {  // tile offsets of the first-generation update kernels
     k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(seg_start, S, tile_base);
     CKL();
     k_scan_exclusive<<<1, 1024, 0, st>>>(tile_base, (int64_t)S + 1, nullptr);
