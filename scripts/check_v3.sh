@@ -5,6 +5,8 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+# does the TMA unit sustain the row gather of k_update_steps3?  (prebuilt binary travels with the snapshot)
+timeout 60 scripts/mb/tma_rows
 # a hang costs its whole timeout in GPU minutes: smoke every switch first with a short leash
 for sw in HB_UPDATE_V3 HB_APPLY_V2 HB_STATS_V2 HB_ASSIGN_V2 HB_DOWNLOAD_MT; do
   env $sw=1 timeout 120 python -c "import __graft_entry__ as g; g.smoke()"
