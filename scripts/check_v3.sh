@@ -6,6 +6,7 @@ set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 # does the TMA unit sustain the row gather of k_update_steps3?  (prebuilt binary travels with the snapshot)
+[ -x scripts/mb/tma_rows ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o scripts/mb/tma_rows scripts/mb/tma_rows.cu
 timeout 60 scripts/mb/tma_rows
 # a hang costs its whole timeout in GPU minutes: smoke every switch first with a short leash
 for sw in HB_UPDATE_V3 HB_APPLY_V2 HB_STATS_V2 HB_ASSIGN_V2 HB_DOWNLOAD_MT; do
