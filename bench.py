@@ -411,6 +411,7 @@ def main():
                 "config": {"workload": f"synthetic {N_global} cells x {D} PCs, 1 covariate ({B_LEVELS} batches), "
                                        f"K={K}, T={T}, block_size=0.05 (BASELINE.json config 3 per GPU)",
                            "cells_per_gpu": n_local, "parallelism": f"cells sharded x{world}",
+                           "switches": sorted(k for k in os.environ if k.startswith("HB_")),  # experimental paths, if any
                            "l2": "state (U,R,Z = 1.2 GB per GPU) is ~10x larger than the 126 MB L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline,
