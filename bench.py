@@ -317,7 +317,7 @@ def main():
     # ---- per-kernel timing pass (region timers: CUDA events on the library stream, extra syncs) -> roofline
     peaks, peak_kind = measured_peaks()
     g.enable_timing(True)
-    names = ("k_update_steps", "k_update_finalize", "k_block_update", "k_block_colsum", "k_step_prepare", "assign",
+    names = ("k_update_steps", "k_rem_sums", "k_update_finalize", "k_block_update", "k_block_colsum", "k_step_prepare", "assign",
              "plan", "ridge_stats", "ridge_solve", "ridge_apply", "update_R")
     base = {r: g.region_time(r) for r in names}
     prof_steps = 3

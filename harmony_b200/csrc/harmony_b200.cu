@@ -28,7 +28,7 @@
 
 #include "kernels.cuh"
 #include "update_kernel.cuh"
-#include "update_kernel3.cuh"
+#include "update_kernel4.cuh"
 #include "assign_tc.cuh"
 #include "assign_tc2.cuh"
 #include "apply_tc.cuh"
@@ -205,16 +205,6 @@ int my_ceil(float num) {
   return inum + 1;
 }
 
-// exchange area of the v3 update kernel (see setup_peer_exchange)
-struct XchArea {
-  int device = 0, world = 0, rank = 0;
-  size_t entries = 0, XH = 0;
-  float* base = nullptr;
-  void* peer[U3_MAXWORLD] = {};
-  unsigned epoch = 0;
-  bool leased = false;
-};
-
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -290,11 +280,11 @@ struct hb_handle {
   bool legacy_centroid = false;  // HB_LEGACY_CENTROID_STEP: centroid update at the top of every clustering round
   DevBuf<float> Rkeep, OEkeep;   // R / O,E saved around the distance-only assignment of that step
   DevBuf<double> objkeep;
-  bool use_v3 = false;  // experimental second-generation update kernel (HB_UPDATE_V3=1)
-  Upd3Geom g3{};
-  bool use_xch = false;  // v3 + sharded cells: block steps exchanged through peer memory (HB_PEER_EXCHANGE=1)
-  Upd3Xch xch{};
-  XchArea* xarea = nullptr;  // leased exchange area (process-wide pool, see setup_peer_exchange)
+  bool use_v4 = false;   // single-pass persistent update kernel (update_kernel4.cuh): the default
+  int u4_nbatch = 0;     // its ring size (batches of U4_BR rows)
+  int plan_nsub = 1;     // third sort key of the plan: block in the next round (nb values) or off (1)
+  DevBuf<float> remT;    // [2][nb][J][KS] next round's removal sums per (block, tuple)
+  DevBuf<int> next_at, chunk_q0, chunk_nq;
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
@@ -598,54 +588,78 @@ int check_convergence_host(hb_handle* h, int type, int* out) {
   return 0;
 }
 
-// ---- update-order plan of round t (buffers hold plan_rounds rounds) ------------------------------
-int build_plan(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, or null */, int set, cudaStream_t st) {
+// ---- update-order plan (buffers hold plan_rounds rounds, two sets) ----------------------------------
+// Phase A: the block of every local cell in round t (harmony.cpp:272-291: position in the shuffled order / cells
+// per block).  Phase B: the round's rows sorted by (block, tuple, block in the next round) + the derived tables.
+int plan_blocks(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, or null */, int set, cudaStream_t st) {
   RegionScope rs(h, "plan");
-  const int nb = h->nb, J = h->J, nc = h->nchunks;
   const int64_t n = h->n;
-  const int S = nb * J;
   const size_t R0 = (size_t)set * h->plan_rounds;  // first round slot of this buffer set
   int* blk_of = h->blk_of.p + (R0 + t) * n;
-  int* order = h->order.p + (R0 + t) * n;
-  int* seg_start = h->seg_start.p + (R0 + t) * (S + 1);
-  int* tile_base = h->tile_base.p + (R0 + t) * (S + 1);
   if (perm_d) {
     CK(cudaMemsetAsync(blk_of, 0xff, sizeof(int) * (size_t)n, st));
     k_plan_block_injected<<<grid_for(h->N_global, 256, h->num_sms * 8), 256, 0, st>>>(
-        perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, nb, blk_of, h->err_flag.p);
+        perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, h->nb, blk_of, h->err_flag.p);
     CKL();
   } else {
     uint64_t key = hb_mix64(h->seed ^ hb_mix64(h->round_counter + 0x1234567ull));
     k_plan_block_native<<<grid_for(n, 256, h->num_sms * 8), 256, 0, st>>>(
-        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, nb, h->half_bits, key, blk_of);
+        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, h->nb, h->half_bits, key, blk_of);
     CKL();
   }
   h->round_counter++;
-  const int wpb = 8;  // warps per block
-  size_t sm = sizeof(int) * (size_t)wpb * nb;
-  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(blk_of, h->chunk_start.p, nc, nb, h->H.p);
+  return 0;
+}
+int plan_sort(hb_handle* h, int t, bool has_next, int set, cudaStream_t st, bool tiles = false) {
+  RegionScope rs(h, "plan");
+  const int nb = h->nb, J = h->J, nc = h->nchunks, nsub = h->plan_nsub;
+  const int64_t n = h->n;
+  const int S = nb * J;
+  const size_t R0 = (size_t)set * h->plan_rounds;
+  const int* blk_of = h->blk_of.p + (R0 + t) * n;
+  const int* blk_next = has_next ? h->blk_of.p + (R0 + t + 1) * n : nullptr;
+  int* order = h->order.p + (R0 + t) * n;
+  int* seg_start = h->seg_start.p + (R0 + t) * (S + 1);
+  int* tile_base = h->tile_base.p + (R0 + t) * (S + 1);
+  const size_t per_warp = sizeof(int) * (size_t)nb * nsub;
+  const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));  // warps per block
+  const size_t sm = per_warp * wpb;
+  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(blk_of, blk_next, h->chunk_start.p, h->chunk_q0.p, h->chunk_nq.p, nc,
+                                                          nb, nsub, h->H.p, h->err_flag.p);
   CKL();
-  k_scan_exclusive<<<1, 1024, 0, st>>>(h->H.p, (int64_t)nb * nc, nullptr);
+  k_scan_exclusive<<<1, 1024, 0, st>>>(h->H.p, (int64_t)nb * nsub * nc, nullptr);
   CKL();
   k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(
-      blk_of, h->chunk_start.p, nc, nb, h->H.p, order, (t > 0) ? h->blk_of.p + (R0 + t - 1) * n : nullptr,
-      h->use_v2 ? h->prev_at.p + (R0 + t) * n : nullptr);
+      blk_of, blk_next, h->chunk_start.p, h->chunk_q0.p, h->chunk_nq.p, nc, nb, nsub, h->H.p, order,
+      (t > 0) ? h->blk_of.p + (R0 + t - 1) * n : nullptr, (h->use_v2 && !h->use_v4) ? h->prev_at.p + (R0 + t) * n : nullptr,
+      h->use_v4 ? h->next_at.p + (R0 + t) * n : nullptr);
   CKL();
-  k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(h->H.p, h->tuple_chunk0.p, nc, nb, J, (int)n,
-                                                                    seg_start, tile_base);
+  k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(h->H.p, h->tuple_chunk0.p, nc, nb, nsub, J, (int)n, seg_start,
+                                                           tile_base);
   CKL();
   if (h->use_v2 && h->aligned_ranges) {
     k_plan_ranges<<<(nb * h->coop_grid + 127) / 128, 128, 0, st>>>(seg_start, nb, J, h->coop_grid,
                                                         h->ranges.p + (R0 + t) * nb * h->coop_grid);
     CKL();
   }
-  if (!h->use_v2 || h->legacy_centroid) {  // tile offsets of the first-generation update kernels
+  if (tiles) {  // tile offsets of the first-generation update kernels
     k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(seg_start, S, tile_base);
     CKL();
     k_scan_exclusive<<<1, 1024, 0, st>>>(tile_base, (int64_t)S + 1, nullptr);
     CKL();
   }
   return 0;
+}
+// all T rounds of a cluster_cpp call (orders: device, T x N_global, or null for the native keyed orders)
+int build_plans(hb_handle* h, int T, const int64_t* orders_d, int set, cudaStream_t st) {
+  for (int t = 0; t < T; ++t) TRY(plan_blocks(h, t, orders_d ? orders_d + (size_t)t * (size_t)h->N_global : nullptr, set, st));
+  for (int t = 0; t < T; ++t) TRY(plan_sort(h, t, t + 1 < T, set, st));
+  return 0;
+}
+// one round into slot 0 of set 0 (per-round paths: first-generation kernels, legacy centroid step)
+int build_plan_single(hb_handle* h, const int64_t* perm_d, cudaStream_t st) {
+  TRY(plan_blocks(h, 0, perm_d, 0, st));
+  return plan_sort(h, 0, false, 0, st, true);
 }
 
 // ---- v1: one update_R sweep (harmony.cpp:269-342), three launches per block step ------------------
@@ -712,109 +726,7 @@ int run_update_R_v1(hb_handle* h, int t) {
   });
 }
 
-// ---- peer-memory exchange area of the v3 update kernel (sharded cells, one node) ------------------
-// Areas live for the life of the process, like the communicators: another rank may still be writing into an
-// area when its owner drops the handle, and unmapping needs a collective that a destructor cannot afford.  A
-// handle leases an area; areas are created collectively, so area i here is paired with area i of every rank.
-constexpr int XCH_MAX_AREAS = 16;
-std::vector<XchArea*> g_xch_areas;
-
-void release_peer_exchange(hb_handle* h) {
-  if (h->xarea) {
-    h->xarea->epoch = h->xch.epoch;  // the next lessee continues the epoch sequence
-    h->xarea->leased = false;
-    h->xarea = nullptr;
-  }
-  h->use_xch = false;
-}
-// Collective over the handle's communicator.  Leases an area all ranks have free, or creates a new one:
-// allocates this rank's part, exchanges the IPC handles and maps the other ranks' parts.  If any rank cannot
-// map a peer the exchange stays off on all ranks (the update then runs one launch + all-reduce per block step).
-int setup_peer_exchange(hb_handle* h, int Tplan) {
-  const int W = h->world;
-  const size_t BK = (size_t)h->B * h->KS, XH = BK + h->KS;
-  const size_t entries = ((size_t)Tplan * h->nb + 2) * 2 * W;
-  // 1. agree on a reusable area: free here AND on every other rank, same shape
-  int64_t freev[XCH_MAX_AREAS + 2];
-  for (int i = 0; i < XCH_MAX_AREAS; ++i) {
-    const XchArea* a = i < (int)g_xch_areas.size() ? g_xch_areas[i] : nullptr;
-    freev[i] = (a && !a->leased && a->device == h->device && a->world == W && a->rank == h->rank && a->entries == entries &&
-                a->XH == XH) ? 1 : 0;
-  }
-  freev[XCH_MAX_AREAS] = (int64_t)g_xch_areas.size();       // min over ranks = smallest pool ...
-  freev[XCH_MAX_AREAS + 1] = -(int64_t)g_xch_areas.size();  // ... and -(largest pool): they must agree
-  DevBuf<int64_t> dv;
-  CK(dv.alloc(XCH_MAX_AREAS + 2));
-  CK(cudaMemcpyAsync(dv.p, freev, sizeof(freev), cudaMemcpyHostToDevice, h->stream));
-  CKN(g_nccl.AllReduce(dv.p, dv.p, XCH_MAX_AREAS + 2, ncclInt64, ncclMin, h->comm, h->stream));
-  CK(cudaMemcpyAsync(freev, dv.p, sizeof(freev), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  XchArea* area = nullptr;
-  for (int i = 0; i < XCH_MAX_AREAS && !area; ++i)
-    if (freev[i] == 1) area = g_xch_areas[i];
-  if (!area) {
-    // every rank sees the same reduced values, so every rank takes the same branch here
-    if (freev[XCH_MAX_AREAS] != -freev[XCH_MAX_AREAS + 1] || freev[XCH_MAX_AREAS] >= XCH_MAX_AREAS) return 0;  // out of step / pool full
-    // 2. create a new area (collective)
-    float* base = nullptr;
-    CK(cudaMalloc((void**)&base, sizeof(float) * (entries * XH + entries)));
-    CK(cudaMemsetAsync(base, 0, sizeof(float) * (entries * XH + entries), h->stream));
-    cudaIpcMemHandle_t mine;
-    CK(cudaIpcGetMemHandle(&mine, base));
-    DevBuf<char> ds, dr;
-    CK(ds.alloc(sizeof(mine)));
-    CK(dr.alloc(sizeof(mine) * W));
-    CK(cudaMemcpyAsync(ds.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
-    CKN(g_nccl.AllGather(ds.p, dr.p, sizeof(mine), ncclChar, h->comm, h->stream));
-    std::vector<cudaIpcMemHandle_t> all(W);
-    CK(cudaMemcpyAsync(all.data(), dr.p, sizeof(mine) * W, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    area = new XchArea();
-    area->device = h->device;
-    area->world = W;
-    area->rank = h->rank;
-    area->entries = entries;
-    area->XH = XH;
-    area->base = base;
-    int64_t ok = 1;
-    for (int r = 0; r < W; ++r) {
-      if (r == h->rank) continue;
-      if (cudaIpcOpenMemHandle(&area->peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        area->peer[r] = nullptr;
-        ok = 0;
-      }
-    }
-    CK(cudaMemcpyAsync(dv.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, h->stream));
-    CKN(g_nccl.AllReduce(dv.p, dv.p, 1, ncclInt64, ncclMin, h->comm, h->stream));
-    CK(cudaMemcpyAsync(&ok, dv.p, sizeof(ok), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    area->leased = !ok;            // an unusable area keeps its index (the ranks stay in step) but is never leased
-    g_xch_areas.push_back(area);
-    if (!ok) {
-      h->warnings.push_back("peer-memory exchange unavailable (CUDA IPC mapping failed); using per-step all-reduce");
-      return 0;
-    }
-  }
-  area->leased = true;
-  h->xarea = area;
-  Upd3Xch& x = h->xch;
-  x.world = W;
-  x.rank = h->rank;
-  x.epoch = area->epoch;
-  x.XH = (int)XH;
-  for (int r = 0; r < W; ++r) {
-    float* base = (r == h->rank) ? area->base : (float*)area->peer[r];
-    x.data[r] = base;
-    x.flag[r] = reinterpret_cast<unsigned*>(base + entries * XH);
-  }
-  x.local_data = x.data[h->rank];
-  x.local_flag = x.flag[h->rank];
-  h->use_xch = true;
-  return 0;
-}
-
-// ---- v2: persistent cooperative kernel over rounds [t0, t1) of this cluster_cpp call --------------
+// ---- persistent update kernels over rounds [t0, t1) of this cluster_cpp call ---------------------------
 int nv_for(int KS) {
   int nv = 1;
   while (4 * UPD_LPR * nv < KS) nv <<= 1;
@@ -869,59 +781,59 @@ UpdArgs make_upd_args(hb_handle* h, int T) {
   a.dbg_cta = h->dbg_cta;
   return a;
 }
+Upd4Args make_upd4_args(hb_handle* h, int T) {
+  Upd4Args a;
+  a.U = h->U.p;
+  a.R = h->R.p;
+  const size_t R0 = (size_t)h->plan_set * h->plan_rounds;
+  a.order = h->order.p + R0 * h->n;
+  a.next_at = h->next_at.p + R0 * h->n;
+  a.ranges = h->ranges.p + R0 * h->nb * h->coop_grid;
+  a.tuple_levels = h->tuple_levels.p;
+  a.sigma = h->sigma.p;
+  a.theta = h->theta.p;
+  a.Pr_b = h->Pr_b.p;
+  a.ring = h->ring.p;
+  a.acc = h->acc2.p;
+  a.remT = h->remT.p;
+  a.OEend = h->OEend.p;
+  a.obj = h->obj2.p;
+  a.bar = h->bar.p;
+  a.n = h->n;
+  a.K = h->K;
+  a.KS = h->KS;
+  a.C = h->C;
+  a.J = h->J;
+  a.B = h->B;
+  a.nb = h->nb;
+  a.T = T;
+  a.s_begin = a.s_end = 0;
+  a.write_from = std::min(T - 1, (int)h->window_size + 1);  // rounds after which cluster_cpp may stop (:250-256)
+  a.has_next_from = T - 1;
+  a.sigma_uniform = h->sigma_uniform ? 1 : 0;
+  a.sigma0 = h->sigma0;
+  a.nbatch = h->u4_nbatch;
+  a.coop = 1;
+  a.dbg = (h->dbg_cta >= 0) ? h->dbg.p : nullptr;
+  a.dbg_cta = h->dbg_cta;
+  return a;
+}
 // zero the per-step accumulators and seed ring[1] (= "O_{-1}") with the current tables
 int upd_begin_call(hb_handle* h, int T) {
   const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
-  if (h->use_xch) h->xch.epoch++;  // flags of earlier calls no longer match
   CK(cudaMemsetAsync(h->acc2.p, 0, sizeof(float) * SL * ((size_t)T * h->nb + 2), h->stream));
   CK(cudaMemsetAsync(h->obj2.p, 0, sizeof(double) * 2 * (size_t)T, h->stream));
   CK(cudaMemsetAsync(h->bar.p, 0, sizeof(unsigned) * 2 * ((size_t)T * h->nb + 2), h->stream));
+  if (h->use_v4) CK(cudaMemsetAsync(h->remT.p, 0, sizeof(float) * h->remT.n, h->stream));
   CK(cudaMemcpyAsync(h->ring.p + 2 * BK, h->O.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->ring.p + 3 * BK, h->E.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   return 0;
 }
-template <int NV>
-int upd3_launch_nv(hb_handle* h, Upd3Args& p, bool cooperative) {
-  const size_t smem = upd3_smem_bytes(h->g3, h->nb);
-  CK(cudaFuncSetAttribute(k_update_steps3<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (cooperative) {
-    void* args[] = {&p};
-    CK(cudaLaunchCooperativeKernel((void*)k_update_steps3<NV>, dim3(h->coop_grid), dim3(U3_THREADS), args, smem, h->stream));
-  } else {
-    k_update_steps3<NV><<<h->coop_grid, U3_THREADS, smem, h->stream>>>(p);
-  }
-  CKL();
-  return 0;
-}
-int upd3_launch(hb_handle* h, const UpdArgs& a, bool cooperative) {
-  Upd3Args p;
-  p.a = a;
-  p.a.use_barrier = cooperative ? 1 : 0;
-  p.g = h->g3;
-  if (h->use_xch) p.x = h->xch;
-  static const bool no_hints = getenv("HB_V3_NO_L2_HINTS") != nullptr;
-  p.l2_hints = no_hints ? 0 : 1;
-  switch (h->g3.NV) {
-    case 1: return upd3_launch_nv<1>(h, p, cooperative);
-    case 2: return upd3_launch_nv<2>(h, p, cooperative);
-    case 3: return upd3_launch_nv<3>(h, p, cooperative);
-    case 4: return upd3_launch_nv<4>(h, p, cooperative);
-    case 5: return upd3_launch_nv<5>(h, p, cooperative);
-  }
-  return fail(h, 2, "update kernel v3: unsupported geometry");
-}
 int upd_launch(hb_handle* h, UpdArgs a, bool cooperative) {
-  if (h->use_v3) return upd3_launch(h, a, cooperative);
   const size_t smem = upd_smem_bytes(h);
   return dispatch_nv(h, h->KS, [&](auto nvc) -> int {
     constexpr int NV = decltype(nvc)::value;
     CK(cudaFuncSetAttribute(k_update_steps<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (h->coop_grid == 0) {
-      int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_update_steps<NV>, UPD_THREADS, smem));
-      if (occ < 1) return fail(h, 2, "persistent update kernel does not fit on an SM");
-      h->coop_grid = h->num_sms;  // one CTA per SM
-    }
     a.use_barrier = cooperative ? 1 : 0;
     if (cooperative) {
       void* args[] = {&a};
@@ -933,21 +845,116 @@ int upd_launch(hb_handle* h, UpdArgs a, bool cooperative) {
     return 0;
   });
 }
-// rounds [t0, t1): t0 == 0 runs the prologue look-ahead.  write_mask: rounds that store R.
+template <int NV>
+int upd4_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
+  const size_t smem = upd4_smem_bytes(NV, a.nbatch, a.KS);
+  CK(cudaFuncSetAttribute(k_update_steps4<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.coop = cooperative ? 1 : 0;
+  if (cooperative) {
+    void* args[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void*)k_update_steps4<NV>, dim3(h->coop_grid), dim3(U4_THREADS), args, smem, h->stream));
+  } else {
+    k_update_steps4<NV><<<h->coop_grid, U4_THREADS, smem, h->stream>>>(a);
+  }
+  CKL();
+  return 0;
+}
+int upd4_launch(hb_handle* h, Upd4Args a, bool cooperative) {
+  switch (upd4_nv(h->KS)) {
+    case 1: return upd4_launch_nv<1>(h, a, cooperative);
+    case 2: return upd4_launch_nv<2>(h, a, cooperative);
+  }
+  return fail(h, 2, "K = %d is not supported by the persistent update kernel", h->K);
+}
+void dump_step_trace(hb_handle* h, int ns, int per_step) {
+  std::vector<long long> st((size_t)(ns + 1) * per_step);
+  if (cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return;
+  cudaStreamSynchronize(h->stream);
+  static int dumped = 0;
+  if (dumped++ != 3) return;
+  FILE* f = fopen("gpurun_out/step_trace.txt", "w");
+  if (!f) return;
+  for (int s = 0; s <= ns; ++s) {
+    fprintf(f, "%d", s);
+    for (int k = 0; k < per_step; ++k) fprintf(f, " %lld", st[(size_t)s * per_step + k]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+}
+// compute_objective() of every round in [t0, t1) (harmony.cpp:248) from the kernels' per-round sums and tables
+int push_round_objectives(hb_handle* h, int t0, int t1) {
+  const size_t BK = (size_t)h->B * h->KS;
+  for (int t = t0; t < t1; ++t) {
+    const float* O = (t == t1 - 1) ? h->O.p : h->OEend.p + (size_t)t * 2 * BK;
+    const float* E = (t == t1 - 1) ? h->E.p : h->OEend.p + (size_t)t * 2 * BK + BK;
+    TRY(push_objective_from(h, O, E, h->obj2.p + 2 * (size_t)t));
+  }
+  return 0;
+}
+// single-pass kernel (update_kernel4.cuh), rounds [t0, t1)
+int run_update_v4(hb_handle* h, int T, int t0, int t1) {
+  RegionScope rs(h, "update_R");
+  const int nb = h->nb;
+  const size_t BK = (size_t)h->B * h->KS, XH = BK + h->KS, SL = 2 * XH;
+  Upd4Args a = make_upd4_args(h, T);
+  if (t0 == 0) {
+    // removal sums of round 0 from the R in memory (assignment step / user), harmony.cpp:312-313
+    RegionScope r0(h, "k_rem_sums");
+    k_rem_sums<<<dim3(h->coop_grid, nb), 256, sizeof(float) * 8 * (size_t)h->KS, h->stream>>>(
+        h->R.p, a.order, a.ranges, a.tuple_levels, a.acc, 0, h->coop_grid, h->K, h->KS, h->C, h->B);
+    CKL();
+    if (h->world > 1)
+      for (int j = 0; j < nb; ++j) TRY(allreduce_f(h, h->acc2.p + (size_t)(j + 1) * SL + XH, XH));
+  }
+  if (h->world <= 1) {
+    a.s_begin = t0 * nb;
+    a.s_end = t1 * nb;
+    RegionScope r3(h, "k_update_steps");
+    TRY(upd4_launch(h, a, true));
+  } else {
+    // sharded cells: one launch per block step, the step's add half all-reduced in between; the next round's
+    // removal sums (remT) are all-reduced and folded once per round
+    RegionScope r3(h, "k_update_steps");
+    for (int t = t0; t < t1; ++t) {
+      if (t > 0) {
+        TRY(allreduce_f(h, h->remT.p + (size_t)(t & 1) * nb * h->J * h->KS, (size_t)nb * h->J * h->KS));
+        k_fold_round<<<grid_for((int64_t)nb * h->K, 256, h->num_sms), 256, 0, h->stream>>>(a, t);
+        CKL();
+      }
+      for (int s = t * nb; s < (t + 1) * nb; ++s) {
+        if (s > t0 * nb) TRY(allreduce_f(h, h->acc2.p + (size_t)(s + 1) * SL, XH));  // add_{s-1}
+        a.s_begin = s;
+        a.s_end = s + 1;
+        TRY(upd4_launch(h, a, false));
+      }
+    }
+    TRY(allreduce_f(h, h->acc2.p + (size_t)(t1 * nb + 1) * SL, XH));  // add_{S-1}
+  }
+  if (h->dbg_cta >= 0 && h->world <= 1) dump_step_trace(h, (t1 - t0) * nb, 8);
+  {
+    RegionScope r4(h, "k_update_finalize");
+    k_update_finalize4<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
+    CKL();
+  }
+  return push_round_objectives(h, t0, t1);
+}
+// first persistent generation (update_kernel.cuh): look-ahead + update warp groups; serves plans whose CTA
+// ranges are not tuple-aligned.  rounds [t0, t1): t0 == 0 runs the prologue look-ahead.  write_mask: rounds that store R.
 int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
   RegionScope rs(h, "update_R");
   const int nb = h->nb;
   const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
   UpdArgs a = make_upd_args(h, T);
   a.write_R_mask = write_mask;
-  if (h->world <= 1 || h->use_xch) {
+  if (h->world <= 1) {
     a.s_begin = t0 * nb;
     a.s_end = t1 * nb;
     a.prologue = (t0 == 0) ? 1 : 0;
     RegionScope r3(h, "k_update_steps");
     TRY(upd_launch(h, a, true));
   } else {
-    // NCCL mode: one launch per step, the step's slot [add_{s-1} | rem_s] all-reduced in between
+    // sharded cells: one launch per step, the step's slot [add_{s-1} | rem_s] all-reduced in between
+    RegionScope r3(h, "k_update_steps");
     if (t0 == 0) {
       a.s_begin = a.s_end = 0;
       a.prologue = 1;
@@ -962,42 +969,16 @@ int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
     }
     TRY(allreduce_f(h, h->acc2.p + (size_t)(t1 * nb + 1) * SL, SL));  // slot(S): add_{S-1} (+ look-ahead rem_S)
   }
-  if (h->dbg_cta >= 0 && h->world <= 1) {
-    const int ns = (t1 - t0) * nb;
-    std::vector<long long> st((size_t)(ns + 1) * 16);
-    CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    static int dumped = 0;
-    if (dumped++ == 3) {
-      FILE* f = fopen("gpurun_out/step_trace.txt", "w");
-      if (f) {
-        for (int s = 0; s <= ns; ++s) {
-          fprintf(f, "%d", s - 1);
-          for (int g = 0; g < 2; ++g)
-            for (int k = 0; k < 8; ++k) fprintf(f, " %lld", st[((size_t)s * 2 + g) * 8 + k]);
-          fprintf(f, "\n");
-        }
-        fclose(f);
-      }
-    }
-  }
+  if (h->dbg_cta >= 0 && h->world <= 1) dump_step_trace(h, (t1 - t0) * nb, 16);
   // tables at the end of round t1-1 -> O, E (the chain itself continues from the ring)
   {
     RegionScope r4(h, "k_update_finalize");
-    if (h->use_xch)
-      k_update_finalize3<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, h->xch, t1 * nb, h->O.p, h->E.p);
-    else
-      k_update_finalize<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
+    k_update_finalize<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
     CKL();
   }
-  // compute_objective() of every round in [t0, t1) (harmony.cpp:248)
-  for (int t = t0; t < t1; ++t) {
-    const float* O = (t == t1 - 1) ? h->O.p : h->OEend.p + (size_t)t * 2 * BK;
-    const float* E = (t == t1 - 1) ? h->E.p : h->OEend.p + (size_t)t * 2 * BK + BK;
-    TRY(push_objective_from(h, O, E, h->obj2.p + 2 * (size_t)t));
-  }
-  return 0;
+  return push_round_objectives(h, t0, t1);
 }
+
 
 // ---- moe_correct_ridge_cpp (harmony.cpp:345-638) -------------------------------------------------
 int run_correct(hb_handle* h) {
@@ -1176,6 +1157,7 @@ int check_err_flag(hb_handle* h) {
     cudaMemcpyAsync(h->err_flag.p, &z, sizeof(int), cudaMemcpyHostToDevice, h->stream);
     if (flag == 1) return fail(h, 4, "update order holds an index outside [0, N)");
     if (flag == 2) return fail(h, 5, "inv(): matrix is singular");
+    if (flag == 3) return fail(h, 4, "update order is not a permutation of the cells");
     return fail(h, 6, "device error flag %d", flag);
   }
   return 0;
@@ -1340,7 +1322,6 @@ void hb_destroy(hb_handle* h) {
   if (h->plan_done) cudaEventDestroy(h->plan_done);
   if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
-  release_peer_exchange(h);
   cudaStream_t s = h->stream;
   delete h;  // frees device buffers
   if (s) cudaStreamDestroy(s);
@@ -1589,8 +1570,9 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     }
   }
   // static tiles (<= TM cells of one tuple) and plan chunks (<= CHUNK cells of one tuple)
-  const int CHUNK = 1024;
-  std::vector<int> t_cell0, t_len, t_tuple, c_start, t_chunk0(J, 0);
+  int CHUNK = 1024;  // plan chunks: ~2000 per shard at most (the plan's scan is nb^2 x #chunks long)
+  while (CHUNK < 16384 && N / CHUNK > 2048) CHUNK <<= 1;
+  std::vector<int> t_cell0, t_len, t_tuple, c_start, t_chunk0(J, 0), c_q0, c_nq;
   for (int q = 0; q < J; ++q) {
     for (int64_t s = tstart[q]; s < tstart[q + 1]; s += TM) {
       t_cell0.push_back((int)s);
@@ -1599,6 +1581,11 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     }
     t_chunk0[q] = (int)c_start.size();
     for (int64_t s = tstart[q]; s < tstart[q + 1]; s += CHUNK) c_start.push_back((int)s);
+    const int nq = (int)c_start.size() - t_chunk0[q];
+    for (int i = 0; i < nq; ++i) {
+      c_q0.push_back(t_chunk0[q]);
+      c_nq.push_back(nq);
+    }
   }
   std::vector<int> tc0, tcl, tct;  // 128-cell tiles for the tensor-core kernels
   for (int q = 0; q < J; ++q)
@@ -1608,6 +1595,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
       tct.push_back(q);
     }
   h->tc_ntiles = (int)tc0.size();
+  c_q0.push_back((int)c_start.size());  // the trailing empty chunk is a group of its own
+  c_nq.push_back(1);
   c_start.push_back((int)N);  // start of the trailing empty chunk
   c_start.push_back((int)N);  // and its end
   h->ntiles = (int)t_cell0.size();
@@ -1621,7 +1610,17 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   const int KS = h->KS, DS = h->DS;
   const size_t nK = (size_t)N * KS, nd = (size_t)N * DS, BK = (size_t)B * KS;
   const int Tplan = std::max(1, (int)h->max_iter_kmeans);
-  h->use_v2 = (KS <= 256) && (J <= 8192) && (getenv("HB_UPDATE_V1") == nullptr);
+  // update_R kernels: the single-pass persistent kernel when every CTA's slice of a block can lie inside one
+  // covariate tuple (2 J <= #SMs) and its ring fits shared memory; else the first persistent generation (K <= 256,
+  // <= 8192 tuples, checked against the shared-memory limit); else one launch triple per block step.
+  const size_t smem_limit = (size_t)227 * 1024 - 256;
+  const bool force_v1 = getenv("HB_UPDATE_V1") != nullptr, force_v2 = getenv("HB_UPDATE_V2") != nullptr;
+  h->coop_grid = h->num_sms;  // one persistent CTA per SM
+  h->aligned_ranges = (2 * J <= h->coop_grid);
+  h->u4_nbatch = upd4_nbatch(KS, smem_limit);
+  h->use_v4 = !force_v1 && !force_v2 && h->aligned_ranges && h->u4_nbatch > 0;
+  h->use_v2 = h->use_v4 || (!force_v1 && (KS <= 256) && (J <= 8192) && upd_smem_bytes(h) <= smem_limit);
+  h->plan_nsub = (h->use_v4 && h->nb <= 64) ? h->nb : 1;
   h->plan_rounds = Tplan;
   CK(h->Zo.alloc(nd));
   CK(h->Zc.alloc(nd));
@@ -1668,31 +1667,30 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tuple_chunk0.alloc(J));
   CK(h->blk_of.alloc(2 * (size_t)Tplan * N));
   CK(h->order.alloc(2 * (size_t)Tplan * N));
-  CK(h->prev_at.alloc(2 * (size_t)Tplan * N));
-  CK(h->H.alloc((size_t)h->nb * h->nchunks));
+  if (h->use_v4)
+    CK(h->next_at.alloc(2 * (size_t)Tplan * N));
+  else
+    CK(h->prev_at.alloc(2 * (size_t)Tplan * N));
+  CK(h->H.alloc((size_t)h->nb * h->plan_nsub * h->nchunks));
+  CK(h->chunk_q0.alloc(h->nchunks));
+  CK(h->chunk_nq.alloc(h->nchunks));
   CK(h->seg_start.alloc(2 * (size_t)Tplan * ((size_t)h->nb * J + 1)));
   CK(h->tile_base.alloc(2 * (size_t)Tplan * ((size_t)h->nb * J + 1)));
   if (h->use_v2) {
     CK(h->ring.alloc(4 * BK));
     CK(h->acc2.alloc(2 * (BK + KS) * ((size_t)Tplan * h->nb + 2)));
-    CK(h->Psave.alloc(2 * (size_t)h->nb * BK));
+    CK(h->Psave.alloc(h->use_v4 ? 1 : 2 * (size_t)h->nb * BK));
+    if (h->use_v4) CK(h->remT.alloc(2 * (size_t)h->nb * J * KS));
     CK(h->OEend.alloc((size_t)Tplan * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)Tplan));
     CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));
-    h->coop_grid = h->num_sms;  // one persistent CTA per SM
-    h->aligned_ranges = (2 * J <= h->coop_grid);
     if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)Tplan * h->nb * h->coop_grid));
-    h->use_v3 = h->aligned_ranges && getenv("HB_UPDATE_V3") != nullptr &&
-                upd3_geometry(KS, h->nb, (size_t)227 * 1024 - 256, &h->g3);  // else: default kernel
-    release_peer_exchange(h);
-    if (h->use_v3 && h->world > 1 && h->world <= U3_MAXWORLD && getenv("HB_PEER_EXCHANGE") != nullptr)
-      TRY(setup_peer_exchange(h, Tplan));
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
       CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));
       CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * (size_t)(32 * h->nb + 2) * 16, h->stream));
     }
-    CK(cudaMemsetAsync(h->Psave.p, 0, sizeof(float) * 2 * (size_t)h->nb * BK, h->stream));
+    CK(cudaMemsetAsync(h->Psave.p, 0, sizeof(float) * h->Psave.n, h->stream));
     CK(cudaMemsetAsync(h->ring.p, 0, sizeof(float) * 4 * BK, h->stream));
   }
   lap.mark("device allocations");
@@ -1720,6 +1718,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   UP(tc_len, tcl);
   UP(tc_tuple, tct);
   UP(chunk_start, c_start);
+  UP(chunk_q0, c_q0);
+  UP(chunk_nq, c_nq);
   UP(tuple_chunk0, t_chunk0);
   {
     std::vector<float> f(K);
@@ -1886,7 +1886,10 @@ int ensure_plan_rounds(hb_handle* h, int T) {
   const size_t S1 = (size_t)h->nb * h->J + 1;
   CK(h->blk_of.alloc(2 * (size_t)T * h->n));
   CK(h->order.alloc(2 * (size_t)T * h->n));
-  CK(h->prev_at.alloc(2 * (size_t)T * h->n));
+  if (h->use_v4)
+    CK(h->next_at.alloc(2 * (size_t)T * h->n));
+  else
+    CK(h->prev_at.alloc(2 * (size_t)T * h->n));
   CK(h->seg_start.alloc(2 * (size_t)T * S1));
   CK(h->tile_base.alloc(2 * (size_t)T * S1));
   if (h->use_v2) {
@@ -1909,8 +1912,9 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
     TRY(run_assign(h, true));
     CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));  // the cold start does not evaluate the objective
   }
-  if (T > 31 && h->use_v2) return fail(h, 2, "max_iter_kmeans > 31 is not supported");
   TRY(ensure_plan_rounds(h, (int)std::max(1u, T)));
+  // the first persistent generation keeps its R-store rounds in a 32-bit mask: longer calls run the per-round path
+  const bool persistent = h->use_v2 && !h->legacy_centroid && (h->use_v4 || T <= 31);
   if (update_orders && T > 0) {
     size_t cnt = (size_t)T * (size_t)h->N_global;
     if (h->perms_d.n < cnt) CK(h->perms_d.alloc(cnt));
@@ -1928,7 +1932,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
     for (iter = 0; iter < T; iter++) {
       if (iter > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
       TRY(legacy_centroid_step(h));  // :235-238
-      TRY(build_plan(h, 0, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr, 0, h->stream));
+      TRY(build_plan_single(h, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr, h->stream));
       TRY(run_update_R_v1(h, 0));  // :241
       TRY(push_objective(h));      // :248
       if (iter > h->window_size) {  // :250-256
@@ -1940,7 +1944,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
         }
       }
     }
-  } else if (h->use_v2) {
+  } else if (persistent) {
     // all T update orders are drawn up front (they do not depend on the data), then the rounds run in
     // chunks: [0, window_size + 2) in one launch, afterwards one round per launch (convergence checks)
     // The native orders of a call depend only on (seed, round counter), so the plan of the NEXT call is
@@ -1951,13 +1955,11 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
         h->plan_set ^= 1;  // adopt the prebuilt plan
       } else {
         h->round_counter -= (uint64_t)h->next_T;  // discard it: its rounds were never run
-        for (unsigned t = 0; t < T; ++t)
-          TRY(build_plan(h, (int)t, update_orders ? h->perms_d.p + (size_t)t * (size_t)h->N_global : nullptr, h->plan_set, h->stream));
+        TRY(build_plans(h, (int)T, update_orders ? h->perms_d.p : nullptr, h->plan_set, h->stream));
       }
       h->next_ready = false;
     } else {
-      for (unsigned t = 0; t < T; ++t)
-        TRY(build_plan(h, (int)t, update_orders ? h->perms_d.p + (size_t)t * (size_t)h->N_global : nullptr, h->plan_set, h->stream));
+      TRY(build_plans(h, (int)T, update_orders ? h->perms_d.p : nullptr, h->plan_set, h->stream));
     }
     if (T > 0) TRY(upd_begin_call(h, (int)T));
     unsigned t0 = 0;
@@ -1965,9 +1967,12 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
       unsigned t1 = (t0 == 0) ? std::min(T, h->window_size + 2) : t0 + 1;
       unsigned mask = 0;
       for (unsigned t = t0; t < t1; ++t)
-        if (t == T - 1 || t > h->window_size) mask |= 1u << t;  // rounds after which cluster_cpp may stop
+        if (t < 32 && (t == T - 1 || t > h->window_size)) mask |= 1u << t;  // rounds after which cluster_cpp may stop
       if (t0 > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
-      TRY(run_update_v2(h, (int)T, (int)t0, (int)t1, mask));
+      if (h->use_v4)
+        TRY(run_update_v4(h, (int)T, (int)t0, (int)t1));
+      else
+        TRY(run_update_v2(h, (int)T, (int)t0, (int)t1, mask));
       iter = t1;
       if (t1 - 1 > h->window_size) {  // :250-256
         int conv = 0;
@@ -1977,9 +1982,14 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
       t0 = t1;
     }
   } else {
+    if (h->next_ready) {  // a plan prebuilt by an earlier call on the side stream is not used here
+      CK(cudaStreamWaitEvent(h->stream, h->plan_done, 0));
+      h->round_counter -= (uint64_t)h->next_T;
+      h->next_ready = false;
+    }
     for (iter = 0; iter < T; iter++) {
       if (iter > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
-      TRY(build_plan(h, 0, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr, 0, h->stream));
+      TRY(build_plan_single(h, update_orders ? h->perms_d.p + (size_t)iter * (size_t)h->N_global : nullptr, h->stream));
       TRY(run_update_R_v1(h, 0));  // :241
       TRY(push_objective(h));      // :248
       if (iter > h->window_size) {  // :250-256
@@ -1992,12 +2002,12 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
       }
     }
   }
-  if (h->use_v2 && !h->legacy_centroid && !update_orders && T > 0 && !h->timing && getenv("HB_NO_PLAN_OVERLAP") == nullptr) {
+  if (persistent && !update_orders && T > 0 && !h->timing && getenv("HB_NO_PLAN_OVERLAP") == nullptr) {
     // prebuild the next call's plan into the other buffer set on the side stream; it starts once this
     // call's own (main-stream) plan build and update kernel are done with the shared scan scratch
     CK(cudaEventRecord(h->ev0, h->stream));
     CK(cudaStreamWaitEvent(h->plan_stream, h->ev0, 0));
-    for (unsigned t = 0; t < T; ++t) TRY(build_plan(h, (int)t, nullptr, h->plan_set ^ 1, h->plan_stream));
+    TRY(build_plans(h, (int)T, nullptr, h->plan_set ^ 1, h->plan_stream));
     CK(cudaEventRecord(h->plan_done, h->plan_stream));
     h->next_ready = true;
     h->next_T = (int)T;
@@ -2236,11 +2246,15 @@ int hb_debug_widen(double* out, const float* in, int64_t n, int threads) {
   return p->threads();
 }
 
-// Geometry chooser of the experimental update kernel (test hook, host only).
+// Ring geometry of the persistent update kernel for rows of KS floats (test hook, host only):
+// out = {float4 per lane, ring slots, rows per slot, shared-memory bytes}; 0 if the kernel cannot run the shape.
 int hb_debug_update_geometry(int KS, int nb, int64_t out[9]) {
-  Upd3Geom g{};
-  if (KS <= 0 || (KS & 3) || nb <= 0 || !upd3_geometry(KS, nb, (size_t)227 * 1024 - 256, &g)) return 0;
-  const int64_t v[9] = {g.NV, g.LPR, g.RPI, g.IT, g.SR, g.KP, g.DU, g.DL, (int64_t)upd3_smem_bytes(g, nb)};
+  (void)nb;
+  if (KS <= 0 || (KS & 3)) return 0;
+  const int nbt = upd4_nbatch(KS, (size_t)227 * 1024 - 256);
+  if (nbt <= 0) return 0;
+  const int nv = upd4_nv(KS);
+  const int64_t v[9] = {nv, nbt, U4_BR, (int64_t)upd4_smem_bytes(nv, nbt, KS), U4_NP, U4_NW, U4_DEPTH, 0, 0};
   for (int i = 0; i < 9; ++i) out[i] = v[i];
   return 1;
 }

@@ -381,20 +381,39 @@ __global__ void k_plan_block_native(int64_t N_global, int64_t cell_offset, int64
     blk_of[s] = (int)b;
   }
 }
-// One warp per chunk (<= chunk cells of one tuple): H[blk][chunk] = #cells of the chunk in block blk.
-__global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restrict__ chunk_start, int nchunks,
-                            int nb, int* __restrict__ H) {
+// Sort key of a cell in round t: (block in round t, tuple, block in round t+1, chunk, cell).  Chunks are runs of
+// consecutive (tuple-sorted) cells of one tuple, so with the histogram laid out as
+//   H[blk][ nsub * cq0[c] + sub * cnq[c] + (c - cq0[c]) ]      (cq0 / cnq: first chunk / #chunks of c's tuple)
+// one plain exclusive scan of H yields the offsets of that order (nsub = nb, sub = next-round block; nsub = 1
+// switches the third key off).
+__device__ __forceinline__ size_t plan_hidx(int blk, int sub, int c, int nchunks, int nsub, const int* __restrict__ cq0,
+                                            const int* __restrict__ cnq) {
+  const int c0 = cq0[c];
+  return (size_t)blk * nsub * nchunks + (size_t)nsub * c0 + (size_t)sub * cnq[c] + (c - c0);
+}
+// One warp per chunk: H[..] = #cells of the chunk with (block, next-round block) = (blk, sub).
+__global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restrict__ blk_next,
+                            const int* __restrict__ chunk_start, const int* __restrict__ cq0, const int* __restrict__ cnq,
+                            int nchunks, int nb, int nsub, int* __restrict__ H, int* __restrict__ err_flag) {
   extern __shared__ int sh[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int* cnt = sh + warp * nb;
+  int* cnt = sh + warp * nb * nsub;
   int c = blockIdx.x * (blockDim.x >> 5) + warp;
   if (c >= nchunks) return;
-  for (int j = lane; j < nb; j += 32) cnt[j] = 0;
+  for (int j = lane; j < nb * nsub; j += 32) cnt[j] = 0;
   __syncwarp();
   int s0 = chunk_start[c], s1 = chunk_start[c + 1];
-  for (int s = s0 + lane; s < s1; s += 32) atomicAdd(cnt + blk_of[s], 1);
+  for (int s = s0 + lane; s < s1; s += 32) {
+    const int b = blk_of[s];
+    if (b < 0 || b >= nb) {  // an injected update order that is not a permutation left this cell without a block
+      atomicExch(err_flag, 3);
+      continue;
+    }
+    const int sub = (nsub > 1 && blk_next) ? blk_next[s] : 0;
+    atomicAdd(cnt + b * nsub + ((sub >= 0 && sub < nsub) ? sub : 0), 1);
+  }
   __syncwarp();
-  for (int j = lane; j < nb; j += 32) H[(size_t)j * nchunks + c] = cnt[j];
+  for (int j = lane; j < nb * nsub; j += 32) H[plan_hidx(j / nsub, j % nsub, c, nchunks, nsub, cq0, cnq)] = cnt[j];
 }
 // Single-CTA exclusive scan of an int array (in place), total written to *total.
 __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data, int64_t n, int* __restrict__ total) {
@@ -433,42 +452,49 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data,
   }
   if (tid == 0 && total) *total = carry;
 }
-// Stable scatter: order[offset(blk, chunk) + rank] = cell, cells of a chunk visited in ascending order.
-__global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __restrict__ chunk_start, int nchunks,
-                               int nb, const int* __restrict__ Hoff, int* __restrict__ order,
-                               const int* __restrict__ blk_prev, int* __restrict__ prev_at) {
+// Stable scatter: order[offset(key, chunk) + rank] = cell, cells of a chunk visited in ascending order;
+// next_at[same position] = block of the cell in the next round.
+__global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __restrict__ blk_next,
+                               const int* __restrict__ chunk_start, const int* __restrict__ cq0, const int* __restrict__ cnq,
+                               int nchunks, int nb, int nsub, const int* __restrict__ Hoff, int* __restrict__ order,
+                               const int* __restrict__ blk_prev, int* __restrict__ prev_at, int* __restrict__ next_at) {
   extern __shared__ int sh[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int* cur = sh + warp * nb;
+  int* cur = sh + warp * nb * nsub;
   int c = blockIdx.x * (blockDim.x >> 5) + warp;
   if (c >= nchunks) return;
-  for (int j = lane; j < nb; j += 32) cur[j] = Hoff[(size_t)j * nchunks + c];
+  for (int j = lane; j < nb * nsub; j += 32) cur[j] = Hoff[plan_hidx(j / nsub, j % nsub, c, nchunks, nsub, cq0, cnq)];
   __syncwarp();
   int s0 = chunk_start[c], s1 = chunk_start[c + 1];
   for (int base = s0; base < s1; base += 32) {
     int s = base + lane;
     bool act = s < s1;
-    int b = act ? blk_of[s] : -1 - lane;  // inactive lanes get unique keys
-    unsigned m = __match_any_sync(0xffffffffu, b);
+    int b = act ? blk_of[s] : -1;
+    act = act && b >= 0 && b < nb;  // cells without a block were flagged by k_plan_hist
+    int nx = (act && blk_next) ? blk_next[s] : 0;
+    if (nx < 0 || nx >= nb) nx = 0;
+    int key = act ? b * nsub + (nsub > 1 ? nx : 0) : -1 - lane;  // inactive lanes get unique keys
+    unsigned m = __match_any_sync(0xffffffffu, key);
     int rank = __popc(m & ((1u << lane) - 1u));
     int leader = __ffs(m) - 1;
     int start = 0;
     if (act && lane == leader) {
-      start = cur[b];
-      cur[b] = start + __popc(m);
+      start = cur[key];
+      cur[key] = start + __popc(m);
     }
     start = __shfl_sync(0xffffffffu, start, leader);
     if (act) {
       order[start + rank] = s;
       if (prev_at) prev_at[start + rank] = blk_prev ? blk_prev[s] : 0;
+      if (next_at) next_at[start + rank] = nx;
     }
     __syncwarp();
   }
 }
-// Segment (block, tuple) boundaries and tile counts: seg s = blk*J + q.
-//   seg_start[s] = Hoff[blk][first chunk of q];  tiles[s] = ceil(len / TM)   (scanned afterwards)
+// Segment (block, tuple) boundaries: seg s = blk*J + q starts at the offset of (blk, first chunk of q, sub 0).
 __global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restrict__ tuple_chunk0, int nchunks,
-                                int nb, int J, int n_local, int* __restrict__ seg_start, int* __restrict__ tile_base) {
+                                int nb, int nsub, int J, int n_local, int* __restrict__ seg_start,
+                                int* __restrict__ tile_base) {
   int S = nb * J;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x) {
     int v;
@@ -476,9 +502,8 @@ __global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restr
       v = n_local;
     } else {
       int blk = s / J, q = s - blk * J;
-      int c = tuple_chunk0[q];  // first chunk of tuple q (== nchunks when q has no later chunks)
-      // empty tuples cannot occur (every tuple has >= 1 cell), so c < nchunks
-      v = Hoff[(size_t)blk * nchunks + c];
+      int c = tuple_chunk0[q];  // first chunk of tuple q (tuples without local cells point at the first later chunk)
+      v = Hoff[(size_t)blk * nsub * nchunks + (size_t)nsub * c];
     }
     seg_start[s] = v;
   }

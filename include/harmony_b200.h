@@ -151,9 +151,10 @@ uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse);
 /* Test hook (host only): the host worker pool of the threaded download path (HB_DOWNLOAD_MT=1) widens n floats to
  * doubles; `threads` sizes the pool on first use (<= 0: HB_HOST_THREADS or the core count).  Returns the pool size. */
 int hb_debug_widen(double* out, const float* in, int64_t n, int threads);
-/* Test hook (host only): lane / stage geometry the experimental update kernel (HB_UPDATE_V3=1) would use for
- * rows of KS floats and nb blocks: out = {NV, LPR, RPI, IT, SR, KP, DU, DL, shared-memory bytes}.  Returns 1 if
- * the shape is supported, 0 if the library would fall back to the default kernel. */
+/* Test hook (host only): ring geometry of the persistent update_R kernel for rows of KS floats:
+ * out = {float4 per lane, ring slots, rows per slot, shared-memory bytes, producer warps, consumer warps, cp.async
+ * groups in flight per producer, 0, 0}.  Returns 1 if the shape is supported, 0 if the library would use the
+ * per-step kernels. */
 int hb_debug_update_geometry(int KS, int nb, int64_t out[9]);
 
 #ifdef __cplusplus

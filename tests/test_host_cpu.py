@@ -146,30 +146,26 @@ def test_native_update_order_is_a_permutation(n):
         assert cnt.min() > 0.5 * len(pos) / 20 and cnt.max() < 1.6 * len(pos) / 20
 
 
-@pytest.mark.parametrize("nb", [1, 5, 20, 100])
-def test_update_v3_geometry_covers_every_row_width(nb):
-    """Lane / stage geometry of the experimental update kernel (HB_UPDATE_V3): for every padded row width the
-    library either declines (falls back to the default kernel) or returns a layout whose lanes cover the row,
-    whose stages can be fed by one producer lane per row and whose rings fit in shared memory."""
+def test_update_kernel_ring_geometry():
+    """Ring geometry of the persistent update kernel: for every padded row width the library either declines
+    (the per-step kernels serve the shape) or returns a ring that fits shared memory, whose lanes cover the row and
+    whose slots split evenly among the producer warps with room for their unpublished batches."""
     import ctypes
     L = _lib.lib()
     out = (ctypes.c_int64 * 9)()
     supported = 0
     for KS in range(4, 1025, 4):
-        if not L.hb_debug_update_geometry(KS, nb, out):
+        if not L.hb_debug_update_geometry(KS, 20, out):
             continue
         supported += 1
-        NV, LPR, RPI, IT, SR, KP, DU, DL, smem = list(out)
-        assert 1 <= NV <= 5 and 1 <= LPR <= 32 and RPI == 32 // LPR and RPI >= 1
-        assert NV * LPR * 4 == KP and KP >= KS                 # the lanes' float4 slots cover the row
-        assert (NV - 1) * LPR * 4 < KS                         # no slot column is entirely padding
-        assert SR == RPI * IT and 1 <= SR <= 32                # one producer lane per staged row
-        assert DU >= 2 and DL >= 2 and smem <= 227 * 1024 - 256
-        assert (KS * 4) % 16 == 0 and (KP * 4) % 16 == 0       # bulk-copy size / row alignment
-    assert not L.hb_debug_update_geometry(6, nb, out)          # row widths are multiples of 4 floats
-    if nb <= 20:
-        assert L.hb_debug_update_geometry(100, nb, out) and list(out)[:3] == [5, 5, 6]   # K = 100: 5 lanes x 5 float4
-        assert supported >= 100
+        NV, nbatch, BR, smem, NP, NW, depth = list(out)[:7]
+        assert NV in (1, 2) and 128 * NV >= KS and (NV == 1 or 128 < KS)   # lane l owns float4 l + 32 v
+        assert nbatch % NP == 0 and nbatch >= 2 * depth
+        assert smem <= 227 * 1024 - 256 and smem >= nbatch * BR * KS * 4
+    assert not L.hb_debug_update_geometry(6, 20, out)          # row widths are multiples of 4 floats
+    assert L.hb_debug_update_geometry(100, 20, out) and out[0] == 1 and out[1] * out[2] >= 400   # K = 100: > 1 block step of rows
+    assert L.hb_debug_update_geometry(200, 20, out) and out[0] == 2
+    assert supported >= 50
 
 
 def test_host_widen_pool_matches_numpy():
