@@ -2254,7 +2254,7 @@ int hb_debug_update_geometry(int KS, int nb, int64_t out[9]) {
   const int nbt = upd4_nbatch(KS, (size_t)227 * 1024 - 256);
   if (nbt <= 0) return 0;
   const int nv = upd4_nv(KS);
-  const int64_t v[9] = {nv, nbt, U4_BR, (int64_t)upd4_smem_bytes(nv, nbt, KS), U4_NP, U4_NW, U4_DEPTH, 0, 0};
+  const int64_t v[9] = {nv, nbt, U4_BR, (int64_t)upd4_smem_bytes(nv, nbt, KS), U4_NP, U4_NW, U4_MINBATCH, 0, 0};
   for (int i = 0; i < 9; ++i) out[i] = v[i];
   return 1;
 }

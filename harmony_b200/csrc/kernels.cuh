@@ -406,7 +406,7 @@ __global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restric
   for (int s = s0 + lane; s < s1; s += 32) {
     const int b = blk_of[s];
     if (b < 0 || b >= nb) {  // an injected update order that is not a permutation left this cell without a block
-      atomicExch(err_flag, 3);
+      atomicCAS(err_flag, 0, 3);  // an out-of-range index (flag 1) is the more specific report
       continue;
     }
     const int sub = (nsub > 1 && blk_next) ? blk_next[s] : 0;
@@ -415,42 +415,46 @@ __global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restric
   __syncwarp();
   for (int j = lane; j < nb * nsub; j += 32) H[plan_hidx(j / nsub, j % nsub, c, nchunks, nsub, cq0, cnq)] = cnt[j];
 }
-// Single-CTA exclusive scan of an int array (in place), total written to *total.
+// Single-CTA exclusive scan of an int array (in place), total written to *total.  Every warp owns a contiguous
+// range and walks it 32 consecutive elements at a time (coalesced): pass 1 sums, pass 2 scans with a carry.
 __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data, int64_t n, int* __restrict__ total) {
   __shared__ int wsum[32];
-  __shared__ int carry;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
-  const int64_t lo = (int64_t)tid * per, hi = (lo + per < n) ? lo + per : n;
+  __shared__ int carry_all;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int64_t per = ((n + nw - 1) / nw + 31) & ~(int64_t)31;
+  const int64_t lo = (int64_t)warp * per, hi = (lo + per < n) ? lo + per : n;
   int s = 0;
-  for (int64_t i = lo; i < hi; ++i) s += data[i];
-  int incl = s;
+  for (int64_t i = lo + lane; i < hi; i += 32) s += data[i];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[warp] = incl;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) wsum[warp] = s;
   __syncthreads();
   if (warp == 0) {
-    int v = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
-    int inc2 = v;
+    int v = (lane < nw) ? wsum[lane] : 0;
+    int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc2, o);
-      if (lane >= o) inc2 += t;
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    wsum[lane] = inc2 - v;
-    if (lane == 31) carry = inc2;
+    wsum[lane] = inc - v;
+    if (lane == 31) carry_all = inc;
   }
   __syncthreads();
-  int base = wsum[warp] + incl - s;
-  for (int64_t i = lo; i < hi; ++i) {
-    int v = data[i];
-    data[i] = base;
-    base += v;
+  int carry = wsum[warp];
+  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const int v = (i < hi) ? data[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (i < hi) data[i] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (tid == 0 && total) *total = carry;
+  if (tid == 0 && total) *total = carry_all;
 }
 // Stable scatter: order[offset(key, chunk) + rank] = cell, cells of a chunk visited in ascending order;
 // next_at[same position] = block of the cell in the next round.

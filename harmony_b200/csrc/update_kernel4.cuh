@@ -15,8 +15,10 @@
 //     gathers 400-byte rows at ~5.3 TB/s; one 1-D bulk/TMA copy per row tops out at 1.3 TB/s, scripts/mb/tma_rows.cu)
 //     into a ring of 8-row batches.  Loads do not depend on the step's tables, so the producers run ahead of the
 //     consumers by the whole ring (>= one block step at K = 100) and HBM streams without gaps across steps.
-//     Completion is published with monotonic counters (cp.async.wait_group + st.release), slots are handed back with
-//     monotonic row counts: no phase parities, nothing to alias.
+//     A batch's arrival is tracked by its slot's mbarrier (cp.async.mbarrier.arrive.noinc: the producers never
+//     block on their own loads, the whole ring can be in flight); slots are handed back with monotonic row counts
+//     and a consumer looks at a slot's mbarrier only after the producer's monotonic `issued` counter says the slot
+//     has entered the use it waits for — a phase parity alone could not tell the wanted refill from the previous one.
 //   * NW consumer warps: one row = one warp (lane l owns columns 4(l+32v)..+3), RU rows in flight per warp.  The
 //     step's penalty row sum_c P[level_c] lives in registers; column sums accumulate in registers and leave through
 //     vector reductions (red.global.add.v4.f32) whenever the next-round block of the rows changes — the plan sorts
@@ -41,7 +43,7 @@ constexpr int U4_NP = 2;                       // producer warps
 constexpr int U4_NW = U4_THREADS / 32 - U4_NP;  // consumer warps
 constexpr int U4_GT = U4_NW * 32;              // consumer threads
 constexpr int U4_BR = 8;                       // rows per ring batch
-constexpr int U4_DEPTH = 8;                    // cp.async groups in flight per producer warp before it publishes
+constexpr int U4_MINBATCH = 16;                // smallest ring worth running (slots)
 constexpr int U4_MAXNV = 2;                    // K <= 128 * U4_MAXNV (wider rows leave no room for a ring)
 
 struct Upd4Args {
@@ -78,16 +80,41 @@ __device__ __forceinline__ unsigned u4_ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ int u4_ld_acquire_cta(const int* p) {
+// Shared-memory hand-shake words.  Deliberately WITHOUT acquire / release qualifiers: a release here would fence the
+// thread's outstanding global reductions and stores (~1 us each time).  What the hand-shakes order is shared-memory
+// traffic only: a slot is handed back after the arithmetic that consumed its rows (data dependence), and a batch's
+// arrival is observed through its mbarrier (acquire by definition).
+__device__ __forceinline__ int u4_ld_volatile(const int* p) {
   int v;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
   return v;
 }
-__device__ __forceinline__ void u4_st_release_cta(int* p, int v) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+__device__ __forceinline__ void u4_st_volatile(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ void u4_red_release_cta(int* p, int v) {
-  asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+__device__ __forceinline__ void u4_red_add_shared(int* p, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void u4_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void u4_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrives once all cp.async operations this thread has issued so far have landed
+__device__ __forceinline__ void u4_cpasync_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool u4_mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void u4_red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -128,10 +155,10 @@ __device__ __forceinline__ void u4_derive(const U4Tables& tv, const float* Pr_b,
   p = u4_penalty_pow(o_eff, e_eff, __ldg(theta + b));
 }
 
-// shared-memory carve-up: tab[2 KP4] | sig[KP4] | part[NW][KP4] | ring[nbatch BR][KS] | cellid[nbatch BR] |
-//   nxt[nbatch BR] | consumed[nbatch] | done[8]      (KP4 = 128 NV floats; everything before the ints is 16-byte aligned)
+// shared-memory carve-up: tab[2 KP4] | sig[KP4] | part[NW][KP4] | ring[nbatch BR][KS] | full[nbatch] (mbarriers) |
+//   cellid[nbatch BR] | nxt[nbatch BR] | consumed[nbatch] | issued[8]      (KP4 = 128 NV floats)
 __host__ __device__ inline size_t upd4_fixed_bytes(int NV, int nbatch) {
-  return sizeof(float) * ((size_t)128 * NV * (3 + U4_NW)) + sizeof(int) * ((size_t)nbatch * (2 * U4_BR + 1) + 8);
+  return sizeof(float) * ((size_t)128 * NV * (3 + U4_NW)) + 8 * (size_t)nbatch + sizeof(int) * ((size_t)nbatch * (2 * U4_BR + 1) + 8);
 }
 __host__ __device__ inline size_t upd4_smem_bytes(int NV, int nbatch, int KS) {
   return upd4_fixed_bytes(NV, nbatch) + sizeof(float) * (size_t)nbatch * U4_BR * KS;
@@ -141,14 +168,14 @@ __host__ __device__ inline int upd4_nv(int KS) {
   while (128 * nv < KS) nv <<= 1;
   return nv;
 }
-// ring slots that fit `limit` bytes of shared memory: a multiple of U4_NP (a slot always belongs to the same
-// producer), at least 2 * U4_DEPTH so that the producers never starve on their own unpublished batches; 0 = no fit
+// ring slots that fit `limit` bytes of shared memory (a multiple of U4_NP: a slot always belongs to the same
+// producer); 0 = the kernel cannot run this row width
 inline int upd4_nbatch(int KS, size_t limit) {
   const int nv = upd4_nv(KS);
   if (nv > U4_MAXNV) return 0;
   int nbt = 512;
-  while (nbt >= 2 * U4_DEPTH && upd4_smem_bytes(nv, nbt, KS) > limit) nbt -= U4_NP;
-  return nbt >= 2 * U4_DEPTH ? nbt : 0;
+  while (nbt >= U4_MINBATCH && upd4_smem_bytes(nv, nbt, KS) > limit) nbt -= U4_NP;
+  return nbt >= U4_MINBATCH ? nbt : 0;
 }
 
 template <int NV>
@@ -168,10 +195,11 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
   float* sig = tab + 2 * KP4;
   float* part = sig + KP4;                                  // [NW][KP4]
   float* ringbuf = part + (size_t)U4_NW * KP4;              // [NBT][BR][KS]
-  int* cellid = reinterpret_cast<int*>(ringbuf + (size_t)NBT * U4_BR * KS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ringbuf + (size_t)NBT * U4_BR * KS);  // [NBT] one phase per use of the slot
+  int* cellid = reinterpret_cast<int*>(full + NBT);
   int* nxt = cellid + (size_t)NBT * U4_BR;
   int* consumed = nxt + (size_t)NBT * U4_BR;                // rows handed back per slot, cumulative
-  int* done = consumed + NBT;                               // batches completed per producer warp, cumulative
+  int* issued_w = consumed + NBT;                           // batches issued per producer warp, cumulative
   __shared__ double sh_obj[2];
 
   // stale ring rows are read (with weight 0) by the tail of a row group: they must be finite
@@ -179,8 +207,10 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
   for (int i = tid; i < KP4; i += U4_THREADS) sig[i] = (i < K) ? a.sigma[i] : 0.f;
   for (int i = tid; i < 2 * KP4; i += U4_THREADS) tab[i] = 0.f;
   for (int i = tid; i < NBT; i += U4_THREADS) consumed[i] = 0;
-  if (tid < 8) done[tid] = 0;
+  if (tid < 8) issued_w[tid] = 0;
+  for (int i = tid; i < NBT; i += U4_THREADS) u4_mbar_init(full + i, 33);  // 32 cp.async arrivals + the meta writer
   if (tid == 0) {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sh_obj[0] = 0.0;
     sh_obj[1] = 0.0;
   }
@@ -199,13 +229,8 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
     bool lane_ok[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) lane_ok[v] = (lane + 32 * v) < KS4;
-    int issued = 0, published = 0;  // batches of this warp
-    int gb0 = 0;                    // global batch index of the first batch of the step
-    auto publish = [&](int count) {
-      __syncwarp();
-      if (lane == 0) u4_st_release_cta(done + p, count);
-      published = count;
-    };
+    int issued = 0;  // batches of this warp
+    int gb0 = 0;     // global batch index of the first batch of the step
     for (int s = a.s_begin; s < a.s_end; ++s) {
       int lo, n;
       range_of(s, lo, n);
@@ -230,12 +255,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
         const int gb = gb0 + b;
         const int slot = gb % NBT;
         const int need = U4_BR * (gb / NBT);  // every earlier use of the slot handed back U4_BR rows
-        if (u4_ld_acquire_cta(consumed + slot) < need) {
-          // the ring is full: everything issued so far must become visible before this warp blocks
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          if (published != issued) publish(issued);
-          while (u4_ld_acquire_cta(consumed + slot) < need) __nanosleep(32);
-        }
+        while (u4_ld_volatile(consumed + slot) < need) __nanosleep(32);
         const int nr = min(U4_BR, n - b * U4_BR);
         float* dst = ringbuf + (size_t)slot * U4_BR * KS;
 #pragma unroll
@@ -251,21 +271,21 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
               }
           }
         }
+        u4_cpasync_arrive(full + slot);
         if (lane < U4_BR) {
           cellid[slot * U4_BR + lane] = cell;
           nxt[slot * U4_BR + lane] = nx;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        __syncwarp();
         ++issued;
-        if (issued - published >= U4_DEPTH) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(U4_DEPTH - 1) : "memory");
-          publish(issued - (U4_DEPTH - 1));
+        if (lane == 0) {
+          u4_mbar_arrive(full + slot);          // release: the meta words above are visible with the phase
+          u4_st_volatile(issued_w + p, issued);  // the slot has entered this use: its parity may be looked at
         }
       }
       gb0 += nbt;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (published != issued) publish(issued);
+    asm volatile("cp.async.wait_all;" ::: "memory");
     return;
   }
 
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
       auto hand_back = [&]() {
         if (rel_b >= 0 && rel_cnt > 0) {
           __syncwarp();
-          if (lane == 0) u4_red_release_cta(consumed + (gb0 + rel_b) % NBT, rel_cnt);
+          if (lane == 0) u4_red_add_shared(consumed + (gb0 + rel_b) % NBT, rel_cnt);
         }
         rel_cnt = 0;
       };
@@ -454,11 +474,16 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
           ++ready_b;
           if (ready_b < r / U4_BR) continue;  // batches before this warp's first row belong to other warps
           const int gb = gb0 + ready_b;
-          const int* dn = done + (gb % U4_NP);
+          const int* iw = issued_w + (gb % U4_NP);
           const int want = gb / U4_NP + 1;
-          while (u4_ld_acquire_cta(dn) < want) {
+          while (u4_ld_volatile(iw) < want) {
+          }
+          uint64_t* fb = full + gb % NBT;
+          const unsigned par = (unsigned)(gb / NBT) & 1u;
+          while (!u4_mbar_try_wait(fb, par)) {
           }
         }
+        if (r == r0) stamp(s, 3);
         float4 u[RU][NV], e[RU][NV];
         float ssum[RU], Aacc[RU], Bacc[RU], Sacc[RU];
         int cellr[RU], nbr[RU];

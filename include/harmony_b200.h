@@ -153,7 +153,7 @@ uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse);
 int hb_debug_widen(double* out, const float* in, int64_t n, int threads);
 /* Test hook (host only): ring geometry of the persistent update_R kernel for rows of KS floats:
  * out = {float4 per lane, ring slots, rows per slot, shared-memory bytes, producer warps, consumer warps, cp.async
- * groups in flight per producer, 0, 0}.  Returns 1 if the shape is supported, 0 if the library would use the
+ * smallest ring (slots), 0, 0}.  Returns 1 if the shape is supported, 0 if the library would use the
  * per-step kernels. */
 int hb_debug_update_geometry(int KS, int nb, int64_t out[9]);
 

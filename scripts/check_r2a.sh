@@ -5,7 +5,7 @@ set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" || exit 1
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_runharmony.py -x -q -m gpu -k "not large" 2>&1 | tail -40
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_runharmony.py -x -q -m gpu -k "not large and not guards" 2>&1 | tail -40
 echo "parity exit: $?"
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_v4.json
 HB_UPDATE_V2=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_v2.json

@@ -158,9 +158,9 @@ def test_update_kernel_ring_geometry():
         if not L.hb_debug_update_geometry(KS, 20, out):
             continue
         supported += 1
-        NV, nbatch, BR, smem, NP, NW, depth = list(out)[:7]
+        NV, nbatch, BR, smem, NP, NW, minb = list(out)[:7]
         assert NV in (1, 2) and 128 * NV >= KS and (NV == 1 or 128 < KS)   # lane l owns float4 l + 32 v
-        assert nbatch % NP == 0 and nbatch >= 2 * depth
+        assert nbatch % NP == 0 and nbatch >= minb
         assert smem <= 227 * 1024 - 256 and smem >= nbatch * BR * KS * 4
     assert not L.hb_debug_update_geometry(6, 20, out)          # row widths are multiples of 4 floats
     assert L.hb_debug_update_geometry(100, 20, out) and out[0] == 1 and out[1] * out[2] >= 400   # K = 100: > 1 block step of rows
