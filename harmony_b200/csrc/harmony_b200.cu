@@ -845,24 +845,26 @@ int upd_launch(hb_handle* h, UpdArgs a, bool cooperative) {
     return 0;
   });
 }
-template <int NV>
+template <int NV, bool SIGU>
 int upd4_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
   const size_t smem = upd4_smem_bytes(NV, a.nbatch, a.KS);
-  CK(cudaFuncSetAttribute(k_update_steps4<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_update_steps4<NV, SIGU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.coop = cooperative ? 1 : 0;
   if (cooperative) {
     void* args[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void*)k_update_steps4<NV>, dim3(h->coop_grid), dim3(U4_THREADS), args, smem, h->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_update_steps4<NV, SIGU>, dim3(h->coop_grid), dim3(U4_THREADS), args, smem,
+                                   h->stream));
   } else {
-    k_update_steps4<NV><<<h->coop_grid, U4_THREADS, smem, h->stream>>>(a);
+    k_update_steps4<NV, SIGU><<<h->coop_grid, U4_THREADS, smem, h->stream>>>(a);
   }
   CKL();
   return 0;
 }
 int upd4_launch(hb_handle* h, Upd4Args a, bool cooperative) {
+  const bool su = h->sigma_uniform;  // the default: scalar sigma (objective terms simplify)
   switch (upd4_nv(h->KS)) {
-    case 1: return upd4_launch_nv<1>(h, a, cooperative);
-    case 2: return upd4_launch_nv<2>(h, a, cooperative);
+    case 1: return su ? upd4_launch_nv<1, true>(h, a, cooperative) : upd4_launch_nv<1, false>(h, a, cooperative);
+    case 2: return su ? upd4_launch_nv<2, true>(h, a, cooperative) : upd4_launch_nv<2, false>(h, a, cooperative);
   }
   return fail(h, 2, "K = %d is not supported by the persistent update kernel", h->K);
 }

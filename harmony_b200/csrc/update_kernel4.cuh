@@ -178,7 +178,7 @@ inline int upd4_nbatch(int KS, size_t limit) {
   return nbt >= U4_MINBATCH ? nbt : 0;
 }
 
-template <int NV>
+template <int NV, bool SIGU>
 __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int KP4 = 128 * NV;
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
     for (int v = 0; v < NV; ++v) lane_ok[v] = (lane + 32 * v) < KS4;
     int issued = 0;  // batches of this warp
     int gb0 = 0;     // global batch index of the first batch of the step
+    int slot = p % NBT, need = 0;  // ring slot of this warp's next batch (global batch p, p + NP, ..) / rows its earlier uses owe
     for (int s = a.s_begin; s < a.s_end; ++s) {
       int lo, n;
       range_of(s, lo, n);
@@ -252,10 +253,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
           cell_n = __ldg(order + bn * U4_BR + lane);
           nx_n = __ldg(next_at + bn * U4_BR + lane);
         }
-        const int gb = gb0 + b;
-        const int slot = gb % NBT;
-        const int need = U4_BR * (gb / NBT);  // every earlier use of the slot handed back U4_BR rows
-        while (u4_ld_volatile(consumed + slot) < need) __nanosleep(32);
+        while (u4_ld_volatile(consumed + slot) < need) __nanosleep(32);  // every earlier use handed back U4_BR rows
         const int nr = min(U4_BR, n - b * U4_BR);
         float* dst = ringbuf + (size_t)slot * U4_BR * KS;
 #pragma unroll
@@ -282,6 +280,11 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
           u4_mbar_arrive(full + slot);          // release: the meta words above are visible with the phase
           u4_st_volatile(issued_w + p, issued);  // the slot has entered this use: its parity may be looked at
         }
+        slot += U4_NP;                           // this warp's next batch is global batch + NP
+        if (slot >= NBT) {
+          slot -= NBT;
+          need += U4_BR;
+        }
       }
       gb0 += nbt;
     }
@@ -298,7 +301,6 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
   bool lane_ok[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) lane_ok[v] = (lane + 32 * v) < KS4;
-  const bool sig_u = a.sigma_uniform != 0;
 
   auto signal = [&](unsigned* c) {
     u4_gsync();
@@ -454,135 +456,129 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
           }
         }
       };
-      // this warp's rows of the step: a contiguous run, RU rows per iteration
+      // this warp's rows of the step: a contiguous run [r0, r1), walked batch by batch, RU rows per iteration
       int c_rows = (n + U4_NW - 1) / U4_NW;
-      c_rows = (c_rows + RU - 1) / RU * RU;
+      c_rows = (c_rows + RU - 1) / RU * RU;   // even starts: a row pair never straddles two batches
       const int r0 = gw * c_rows, r1 = min(n, r0 + c_rows);
-      int ready_b = -1;   // batches of the step up to here are known to be in shared memory
-      int rel_b = -1, rel_cnt = 0;  // rows of batch rel_b this warp is done with, not yet handed back
-      auto hand_back = [&]() {
-        if (rel_b >= 0 && rel_cnt > 0) {
-          __syncwarp();
-          if (lane == 0) u4_red_add_shared(consumed + (gb0 + rel_b) % NBT, rel_cnt);
-        }
-        rel_cnt = 0;
-      };
-      for (int r = r0; r < r1; r += RU) {
-        const int rlast = min(r + RU, r1) - 1;
-        const int b_hi = rlast / U4_BR;
-        while (ready_b < b_hi) {
-          ++ready_b;
-          if (ready_b < r / U4_BR) continue;  // batches before this warp's first row belong to other warps
-          const int gb = gb0 + ready_b;
-          const int* iw = issued_w + (gb % U4_NP);
-          const int want = gb / U4_NP + 1;
-          while (u4_ld_volatile(iw) < want) {
+      if (r0 < r1) {
+        int b = r0 / U4_BR;                    // batch of the step
+        int gbl = gb0 + b;                     // global batch index
+        int slot = gbl % NBT;
+        unsigned par = (unsigned)(gbl / NBT) & 1u;
+        bool first = true;
+        for (int rb = r0; rb < r1;) {
+          const int bend = min(r1, (b + 1) * U4_BR);
+          {  // the batch has entered this use of its slot (issued), then: its rows have landed (mbarrier phase)
+            const int* iw = issued_w + (gbl % U4_NP);
+            const int want = gbl / U4_NP + 1;
+            while (u4_ld_volatile(iw) < want) {
+            }
+            while (!u4_mbar_try_wait(full + slot, par)) {
+            }
           }
-          uint64_t* fb = full + gb % NBT;
-          const unsigned par = (unsigned)(gb / NBT) & 1u;
-          while (!u4_mbar_try_wait(fb, par)) {
+          if (first) {
+            stamp(s, 3);
+            first = false;
           }
-        }
-        if (r == r0) stamp(s, 3);
-        float4 u[RU][NV], e[RU][NV];
-        float ssum[RU], Aacc[RU], Bacc[RU], Sacc[RU];
-        int cellr[RU], nbr[RU];
-        bool valid[RU];
+          const float* bbase = ringbuf + (size_t)slot * U4_BR * KS;
+          const int* bcell = cellid + slot * U4_BR;
+          const int* bnxt = nxt + slot * U4_BR;
+          const int handed = bend - rb + ((bend == n) ? nbt * U4_BR - n : 0);  // + the step's padding rows
+          for (int k = rb - b * U4_BR; rb < bend; rb += RU, k += RU) {
+            float4 u[RU][NV], e[RU][NV];
+            float ssum[RU], Aacc[RU], Bacc[RU], Sacc[RU];
+            int cellr[RU], nbr[RU];
+            bool valid[RU];
 #pragma unroll
-        for (int i = 0; i < RU; ++i) {
-          const int row = r + i;
-          valid[i] = row < r1;
-          const int rowc = valid[i] ? row : rlast;
-          const int sr = ((gb0 + rowc / U4_BR) % NBT) * U4_BR + (rowc % U4_BR);
-          cellr[i] = cellid[sr];
-          nbr[i] = nxt[sr];
-          const float* rp = ringbuf + (size_t)sr * KS;
+            for (int i = 0; i < RU; ++i) {
+              valid[i] = (i == 0) || (rb + i < bend);
+              const int kk = valid[i] ? k + i : k;
+              cellr[i] = bcell[kk];
+              nbr[i] = bnxt[kk];
+              const float* rp = bbase + (size_t)kk * KS;
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            u[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane_ok[v]) u[i][v] = *reinterpret_cast<const float4*>(rp + 4 * (lane + 32 * v));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < RU; ++i) {
-          ssum[i] = Aacc[i] = Bacc[i] = Sacc[i] = 0.f;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            const float uu[4] = {u[i][v].x, u[i][v].y, u[i][v].z, u[i][v].w};
-            const float pp[4] = {pP[v].x, pP[v].y, pP[v].z, pP[v].w};
-            const float ll[4] = {pL[v].x, pL[v].y, pL[v].z, pL[v].w};
-            const float ss[4] = {sg[v].x, sg[v].y, sg[v].z, sg[v].w};
-            float ee[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              ee[c] = fast_exp(uu[c]) * pp[c];  // un-normalised R (>= 0; exactly 0 in the padding columns)
-              if (sig_u) {
-                Aacc[i] = fmaf(ee[c], uu[c], Aacc[i]);
-                Bacc[i] = fmaf(ee[c], ll[c], Bacc[i]);
-              } else {
-                const float tt = ss[c] * ee[c];
-                Aacc[i] = fmaf(tt, uu[c], Aacc[i]);
-                Bacc[i] = fmaf(tt, ll[c], Bacc[i]);
-                Sacc[i] += tt;
+              for (int v = 0; v < NV; ++v) {
+                u[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane_ok[v]) u[i][v] = *reinterpret_cast<const float4*>(rp + 4 * (lane + 32 * v));
               }
             }
-            ssum[i] += (ee[0] + ee[1]) + (ee[2] + ee[3]);
-            e[i][v] = make_float4(ee[0], ee[1], ee[2], ee[3]);
-          }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+            for (int i = 0; i < RU; ++i) {
+              ssum[i] = Aacc[i] = Bacc[i] = Sacc[i] = 0.f;
 #pragma unroll
-          for (int i = 0; i < RU; ++i) ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], o);
+              for (int v = 0; v < NV; ++v) {
+                const float uu[4] = {u[i][v].x, u[i][v].y, u[i][v].z, u[i][v].w};
+                const float pp[4] = {pP[v].x, pP[v].y, pP[v].z, pP[v].w};
+                const float ll[4] = {pL[v].x, pL[v].y, pL[v].z, pL[v].w};
+                const float ss[4] = {sg[v].x, sg[v].y, sg[v].z, sg[v].w};
+                float ee[4];
 #pragma unroll
-        for (int i = 0; i < RU; ++i) {
-          const float sdiv = (ssum[i] == 0.f) ? 1.f : ssum[i];  // arma::normalise(.., 1, 0): zero norm divides by 1
-          const float inv = valid[i] ? fast_rcp(sdiv) : 0.f;
-          if (valid[i] && nbr[i] != cur_nb) {  // warp-uniform
-            flush_next();
-            cur_nb = nbr[i];
-          }
-          float* rp = a.R + (size_t)cellr[i] * KS;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            float4 rr;
-            rr.x = e[i][v].x * inv;
-            rr.y = e[i][v].y * inv;
-            rr.z = e[i][v].z * inv;
-            rr.w = e[i][v].w * inv;
-            cs2[v].x += rr.x;
-            cs2[v].y += rr.y;
-            cs2[v].z += rr.z;
-            cs2[v].w += rr.w;
-            if (writeR && valid[i] && lane_ok[v]) *reinterpret_cast<float4*>(rp + 4 * (lane + 32 * v)) = rr;
-          }
-          // sum_k R dist = -sum sigma R U ;  sum_k sigma R log R = sum sigma R (U + log Psum - log s)
-          const float ls = fast_log(sdiv);
-          if (sig_u) {
-            const float srow = (lane == 0) ? ssum[i] : 0.f;  // the row total once per row
-            const float w = a.sigma0 * inv;
-            okd = fmaf(-w, Aacc[i], okd);
-            oent = fmaf(w, (Aacc[i] + Bacc[i]) - ls * srow, oent);
-          } else {
-            okd = fmaf(-inv, Aacc[i], okd);
-            oent = fmaf(inv, (Aacc[i] + Bacc[i]) - ls * Sacc[i], oent);
-          }
-        }
-        // hand finished rows back to the producers, batch by batch
-#pragma unroll
-        for (int i = 0; i < RU; ++i) {
-          if (valid[i]) {
-            const int bi = (r + i) / U4_BR;
-            if (bi != rel_b) {
-              hand_back();
-              rel_b = bi;
+                for (int c = 0; c < 4; ++c) {
+                  ee[c] = fast_exp(uu[c]) * pp[c];  // un-normalised R (>= 0; exactly 0 in the padding columns)
+                  if (SIGU) {
+                    Aacc[i] = fmaf(ee[c], uu[c], Aacc[i]);
+                    Bacc[i] = fmaf(ee[c], ll[c], Bacc[i]);
+                  } else {
+                    const float tt = ss[c] * ee[c];
+                    Aacc[i] = fmaf(tt, uu[c], Aacc[i]);
+                    Bacc[i] = fmaf(tt, ll[c], Bacc[i]);
+                    Sacc[i] += tt;
+                  }
+                }
+                ssum[i] += (ee[0] + ee[1]) + (ee[2] + ee[3]);
+                e[i][v] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+              }
             }
-            ++rel_cnt;
-            if (r + i == n - 1) rel_cnt += nbt * U4_BR - n;  // the padding rows of the step's last batch
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int i = 0; i < RU; ++i) ssum[i] += __shfl_xor_sync(0xffffffffu, ssum[i], o);
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+              const float sdiv = (ssum[i] == 0.f) ? 1.f : ssum[i];  // arma::normalise(.., 1, 0): zero norm divides by 1
+              const float inv = valid[i] ? fast_rcp(sdiv) : 0.f;
+              if (valid[i] && nbr[i] != cur_nb) {  // warp-uniform
+                flush_next();
+                cur_nb = nbr[i];
+              }
+              float* rp = a.R + (size_t)cellr[i] * KS;
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+                float4 rr;
+                rr.x = e[i][v].x * inv;
+                rr.y = e[i][v].y * inv;
+                rr.z = e[i][v].z * inv;
+                rr.w = e[i][v].w * inv;
+                cs2[v].x += rr.x;
+                cs2[v].y += rr.y;
+                cs2[v].z += rr.z;
+                cs2[v].w += rr.w;
+                if (writeR && valid[i] && lane_ok[v]) *reinterpret_cast<float4*>(rp + 4 * (lane + 32 * v)) = rr;
+              }
+              // sum_k R dist = -sum sigma R U ;  sum_k sigma R log R = sum sigma R (U + log Psum - log s)
+              const float ls = fast_log(sdiv);
+              if (SIGU) {
+                const float srow = (lane == 0) ? ssum[i] : 0.f;  // the row total once per row
+                const float w = a.sigma0 * inv;
+                okd = fmaf(-w, Aacc[i], okd);
+                oent = fmaf(w, (Aacc[i] + Bacc[i]) - ls * srow, oent);
+              } else {
+                okd = fmaf(-inv, Aacc[i], okd);
+                oent = fmaf(inv, (Aacc[i] + Bacc[i]) - ls * Sacc[i], oent);
+              }
+            }
+          }
+          // hand the rows of this batch back to the producers
+          __syncwarp();
+          if (lane == 0) u4_red_add_shared(consumed + slot, handed);
+          ++b;
+          ++gbl;
+          if (++slot == NBT) {
+            slot = 0;
+            par ^= 1u;
           }
         }
       }
-      hand_back();
       flush_next();
       stamp(s, 4);
       // ---- add_s: this CTA's column sums -> slot(s+1) ----
