@@ -48,6 +48,7 @@ struct Assign3Args {
   float* acc;               // plan mode: accumulator slots of the update kernel, slot(j) at (j + 1) * SL
   double* obj_acc;          // [2] (init only)
   float* Zc_out;            // natural mode + normalise: the normalised rows are stored here (null: not stored)
+  const int* ntiles_ptr;    // plan mode: tile count on the device (the plan is built without a host round trip)
   int ntiles, d, K, C, B, DS, KS;
   int KD;         // reduction length padded to a multiple of 8
   int NP;         // clusters padded to a multiple of 16
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
   const uint32_t tmem = *tmem_slot;
 
   const int my_first = blockIdx.x, stride = gridDim.x;
+  if (a.ntiles_ptr) a.ntiles = __ldg(a.ntiles_ptr);
 
   if (warp == 0) {
     // =============================== gather producer ===============================

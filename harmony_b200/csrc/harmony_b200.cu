@@ -29,8 +29,7 @@
 #include "kernels.cuh"
 #include "update_kernel.cuh"
 #include "update_kernel4.cuh"
-#include "assign_tc.cuh"
-#include "assign_tc2.cuh"
+#include "assign_tc3.cuh"
 #include "apply_tc.cuh"
 #include "apply_tc2.cuh"
 #include "stats_tc.cuh"
@@ -283,6 +282,10 @@ struct hb_handle {
   bool use_v4 = false;   // single-pass persistent update kernel (update_kernel4.cuh): the default
   int u4_nbatch = 0;     // its ring size (batches of U4_BR rows)
   int plan_nsub = 1;     // third sort key of the plan: block in the next round (nb values) or off (1)
+  int assign_ns = 2;     // operand stages of the tensor-core assignment kernel
+  bool zc_pending_norm = false;  // Zc holds the un-normalised corrected embedding although cluster_cpp has run
+  DevBuf<int> pt_p0, pt_len, pt_tuple, pt_blk, pt_count, pt_base;  // [2 sets] 128-row tiles of round 0 in plan order
+  size_t pt_cap = 0;
   DevBuf<float> remT;    // [2][nb][J][KS] next round's removal sums per (block, tuple)
   DevBuf<int> next_at, chunk_q0, chunk_nq;
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
@@ -409,7 +412,8 @@ int dispatch_kq(hb_handle* h, int K, F&& f) {
 }
 
 // ---- K1 launcher: assignment from centroids (init + cold start) -------------------------------
-int run_assign(hb_handle* h, bool normalise) {
+// plan_mode: tiles follow round 0 of the current plan set (tensor-core kernel only); want_obj: objective sums (init)
+int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_obj = true) {
   RegionScope rs(h, "assign");
   const int K = h->K, d = h->d, B = h->B, KS = h->KS;
   const int KP = (K + 63) & ~63, DP4 = (d + 3) & ~3;
@@ -436,68 +440,83 @@ int run_assign(hb_handle* h, bool normalise) {
   a.KS = KS;
   a.normalise = normalise ? 1 : 0;
   if (h->use_tc_assign) {
-    AssignTcArgs t;
+    Assign3Args t{};
     t.Zc = a.Zc;
     t.Y = a.Y;
     t.sigma = a.sigma;
     t.U = a.U;
-    t.R = a.R;
-    t.tile_cell0 = h->tc_cell0.p;
-    t.tile_len = h->tc_len.p;
-    t.tile_tuple = h->tc_tuple.p;
     t.tuple_levels = a.tuple_levels;
-    t.O_acc = a.O_acc;
-    t.rs_acc = a.rs_acc;
     t.obj_acc = a.obj_acc;
-    t.ntiles = h->tc_ntiles;
     t.d = d;
     t.K = K;
     t.C = h->C;
+    t.B = B;
     t.DS = h->DS;
     t.KS = KS;
     t.KD = (d + 7) & ~7;
     t.NP = (K + 15) & ~15;
+    t.SS = assign3_stage_stride(KS);
+    t.ns = h->assign_ns;
     t.normalise = a.normalise;
-    t.dbg = nullptr;
-    static int trace_calls = 0;
-    const bool tracing = getenv("HB_TRACE_ASSIGN") != nullptr && (++trace_calls == 4);
-    if (tracing) {
-      if (h->dbg.n < 64 * 24) CK(h->dbg.alloc(64 * 24));
-      CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 64 * 24, h->stream));
-      t.dbg = h->dbg.p;
-    }
-    const int grid_tc = std::max(1, std::min(h->tc_ntiles, h->num_sms));
-    static const bool assign_v2 = getenv("HB_ASSIGN_V2") != nullptr;  // experimental rewrite (assign_tc2.cuh)
-    if (assign_v2 && !tracing && t.NP <= 128 && assign_tc2_smem_bytes(t.KD, t.NP, h->DS) <= 227 * 1024) {
-      const size_t smem_tc = assign_tc2_smem_bytes(t.KD, t.NP, h->DS);
-      CK(cudaFuncSetAttribute(k_assign_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-      k_assign_tc2<<<grid_tc, A2_THREADS, smem_tc, h->stream>>>(t);
+    t.want_obj = want_obj ? 1 : 0;
+    int grid_tc;
+    if (plan_mode) {
+      // rows in the order of round 0 of the coming cluster_cpp call: a tile's column sums are a share of its block's
+      // removal sums and go to the update kernel's accumulator slots; R is not stored
+      const size_t R0 = (size_t)h->plan_set * h->plan_rounds;
+      const size_t cap = h->pt_cap;
+      t.R = nullptr;
+      t.row_index = h->order.p + R0 * h->n;
+      t.tile_p0 = h->pt_p0.p + (size_t)h->plan_set * cap;
+      t.tile_len = h->pt_len.p + (size_t)h->plan_set * cap;
+      t.tile_tuple = h->pt_tuple.p + (size_t)h->plan_set * cap;
+      t.tile_blk = h->pt_blk.p + (size_t)h->plan_set * cap;
+      t.ntiles_ptr = h->pt_count.p + h->plan_set;
+      t.ntiles = 0;
+      t.acc = h->acc2.p;
+      t.Zc_out = nullptr;
+      grid_tc = h->num_sms;
     } else {
-      const size_t smem_tc = assign_tc_smem_bytes(t.KD, t.NP, KS);
-      CK(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-      k_assign_tc<<<grid_tc, TC_THREADS, smem_tc, h->stream>>>(t);
+      t.R = a.R;
+      t.row_index = nullptr;
+      t.tile_p0 = h->tc_cell0.p;
+      t.tile_len = h->tc_len.p;
+      t.tile_tuple = h->tc_tuple.p;
+      t.tile_blk = nullptr;
+      t.ntiles_ptr = nullptr;
+      t.ntiles = h->tc_ntiles;
+      t.O_acc = a.O_acc;
+      t.rs_acc = a.rs_acc;
+      t.Zc_out = normalise ? h->Zc.p : nullptr;  // the compatibility paths read the normalised embedding back
+      grid_tc = std::max(1, std::min(h->tc_ntiles, h->num_sms));
+    }
+    const size_t smem_tc = assign3_smem_bytes(t.ns, t.KD, t.NP, KS);
+    if (want_obj) {
+      CK(cudaFuncSetAttribute(k_assign_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      k_assign_tc3<true><<<grid_tc, A3_THREADS, smem_tc, h->stream>>>(t);
+    } else {
+      CK(cudaFuncSetAttribute(k_assign_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      k_assign_tc3<false><<<grid_tc, A3_THREADS, smem_tc, h->stream>>>(t);
     }
     CKL();
-    if (tracing) {
-      std::vector<long long> st(64 * 24);
-      CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      if (FILE* f = fopen("gpurun_out/assign_trace.txt", "w")) {
-        for (int i = 0; i < 64; ++i) {
-          fprintf(f, "%d", i);
-          for (int k = 0; k < 24; ++k) fprintf(f, " %lld", st[(size_t)i * 24 + k]);
-          fprintf(f, "\n");
-        }
-        fclose(f);
-      }
-    }
     h->R_user_set = false;
+    if (plan_mode) {
+      // O, E of the assignment = the sums of the blocks' removal terms (harmony.cpp:226-227)
+      const size_t XH = (size_t)B * KS + KS;
+      if (h->world > 1)
+        for (int j = 0; j < h->nb; ++j) TRY(allreduce_f(h, h->acc2.p + (size_t)(j + 1) * 2 * XH + XH, XH));
+      k_assign_finalize_plan<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->acc2.p, h->nb, h->Pr_b.p, h->O.p, h->E.p, B, K, KS);
+      CKL();
+      h->zc_pending_norm = normalise;  // the normalised embedding (harmony.cpp:220) is materialised on demand
+      return 0;
+    }
     TRY(allreduce_f(h, h->Oacc.p, (size_t)B * KS + KS));
     k_assign_finalize<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * KS, h->Pr_b.p,
                                                                     h->O.p, h->E.p, B, K, KS);
     CKL();
     return 0;
   }
+  if (plan_mode) return fail(h, 3, "internal: plan-order assignment without the tensor-core kernel");
   size_t smem = sizeof(float) * ((size_t)DP4 * KP + (size_t)TM * DP4 + (size_t)TM * (KP + 4) + KP + (size_t)NWARP * KP);
   if (smem > 227 * 1024) return fail(h, 2, "K*d too large for the assignment kernel (needs %zu B shared memory)", smem);
   int st = dispatch_kq(h, K, [&](auto kq) -> int {
@@ -654,6 +673,21 @@ int plan_sort(hb_handle* h, int t, bool has_next, int set, cudaStream_t st, bool
 int build_plans(hb_handle* h, int T, const int64_t* orders_d, int set, cudaStream_t st) {
   for (int t = 0; t < T; ++t) TRY(plan_blocks(h, t, orders_d ? orders_d + (size_t)t * (size_t)h->N_global : nullptr, set, st));
   for (int t = 0; t < T; ++t) TRY(plan_sort(h, t, t + 1 < T, set, st));
+  if (T > 0 && h->use_tc_assign && h->use_v4) {
+    // 128-row tiles of round 0, one (block, tuple) segment at a time: the assignment step of the call runs in this order
+    RegionScope rs(h, "plan");
+    const int S = h->nb * h->J;
+    const int* seg_start = h->seg_start.p + (size_t)set * h->plan_rounds * (S + 1);
+    k_plan_tilecount128<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(seg_start, S, h->pt_base.p);
+    CKL();
+    k_scan_exclusive<<<1, 1024, 0, st>>>(h->pt_base.p, (int64_t)S + 1, h->pt_count.p + set);
+    CKL();
+    k_plan_tilefill128<<<grid_for(S, 128, 64), 128, 0, st>>>(seg_start, h->pt_base.p, S, h->J, h->pt_p0.p + (size_t)set * h->pt_cap,
+                                                          h->pt_len.p + (size_t)set * h->pt_cap,
+                                                          h->pt_tuple.p + (size_t)set * h->pt_cap,
+                                                          h->pt_blk.p + (size_t)set * h->pt_cap);
+    CKL();
+  }
   return 0;
 }
 // one round into slot 0 of set 0 (per-round paths: first-generation kernels, legacy centroid step)
@@ -818,13 +852,18 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.dbg_cta = h->dbg_cta;
   return a;
 }
-// zero the per-step accumulators and seed ring[1] (= "O_{-1}") with the current tables
-int upd_begin_call(hb_handle* h, int T) {
+// zero the per-step accumulators of a cluster_cpp call ...
+int upd_begin_zero(hb_handle* h, int T) {
   const size_t BK = (size_t)h->B * h->KS, SL = 2 * (BK + h->KS);
   CK(cudaMemsetAsync(h->acc2.p, 0, sizeof(float) * SL * ((size_t)T * h->nb + 2), h->stream));
   CK(cudaMemsetAsync(h->obj2.p, 0, sizeof(double) * 2 * (size_t)T, h->stream));
   CK(cudaMemsetAsync(h->bar.p, 0, sizeof(unsigned) * 2 * ((size_t)T * h->nb + 2), h->stream));
   if (h->use_v4) CK(cudaMemsetAsync(h->remT.p, 0, sizeof(float) * h->remT.n, h->stream));
+  return 0;
+}
+// ... and seed ring[1] (= "O_{-1}") with the tables the call starts from
+int upd_begin_seed(hb_handle* h) {
+  const size_t BK = (size_t)h->B * h->KS;
   CK(cudaMemcpyAsync(h->ring.p + 2 * BK, h->O.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->ring.p + 3 * BK, h->E.p, sizeof(float) * BK, cudaMemcpyDeviceToDevice, h->stream));
   return 0;
@@ -894,12 +933,12 @@ int push_round_objectives(hb_handle* h, int t0, int t1) {
   return 0;
 }
 // single-pass kernel (update_kernel4.cuh), rounds [t0, t1)
-int run_update_v4(hb_handle* h, int T, int t0, int t1) {
+int run_update_v4(hb_handle* h, int T, int t0, int t1, bool rem_ready) {
   RegionScope rs(h, "update_R");
   const int nb = h->nb;
   const size_t BK = (size_t)h->B * h->KS, XH = BK + h->KS, SL = 2 * XH;
   Upd4Args a = make_upd4_args(h, T);
-  if (t0 == 0) {
+  if (t0 == 0 && !rem_ready) {
     // removal sums of round 0 from the R in memory (assignment step / user), harmony.cpp:312-313
     RegionScope r0(h, "k_rem_sums");
     k_rem_sums<<<dim3(h->coop_grid, nb), 256, sizeof(float) * 8 * (size_t)h->KS, h->stream>>>(
@@ -1663,8 +1702,18 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
                     (getenv("HB_APPLY_FFMA") == nullptr);
   h->use_tc_stats = (K <= 128) && (d + 1 <= 64) && stats_tc_smem_bytes(KS, h->DS) <= 227 * 1024 &&
                     (getenv("HB_STATS_FFMA") == nullptr);
-  h->use_tc_assign = (h->DS <= 4 * TC_DS4MAX) && (KS <= 256) &&
-                     assign_tc_smem_bytes((d + 7) & ~7, (K + 15) & ~15, KS) <= 227 * 1024 && (getenv("HB_ASSIGN_FFMA") == nullptr);
+  h->assign_ns = assign3_smem_bytes(2, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit ? 2 : 1;
+  h->use_tc_assign = (d <= 64) && (K <= 128) && assign3_smem_bytes(h->assign_ns, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit &&
+                     (getenv("HB_ASSIGN_FFMA") == nullptr);
+  h->pt_cap = (size_t)N / TC_TM + (size_t)h->nb * J + 2;
+  if (h->use_tc_assign && h->use_v4) {
+    CK(h->pt_p0.alloc(2 * h->pt_cap));
+    CK(h->pt_len.alloc(2 * h->pt_cap));
+    CK(h->pt_tuple.alloc(2 * h->pt_cap));
+    CK(h->pt_blk.alloc(2 * h->pt_cap));
+    CK(h->pt_count.alloc(2));
+    CK(h->pt_base.alloc((size_t)h->nb * J + 2));
+  }
   CK(h->chunk_start.alloc(h->nchunks + 1));
   CK(h->tuple_chunk0.alloc(J));
   CK(h->blk_of.alloc(2 * (size_t)Tplan * N));
@@ -1798,7 +1847,7 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
   k_normalise_rows<<<grid_for((int64_t)h->K * 32, 256, 64), 256, 0, h->stream>>>(h->Y.p, h->Y.p, h->K, h->d, h->d);
   CKL();
   CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
-  TRY(run_assign(h, false));
+  TRY(run_assign(h, false, false, true));
   TRY(push_objective(h));                       // compute_objective() (:152)
   lap.mark("assignment + objective");
   h->harmony_slots.push_back(h->obj_count - 1);  // objective_harmony.push_back (:153)
@@ -1910,13 +1959,17 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
   if (!h->ran_init) return fail(h, 3, "init_cluster_cpp has not been run");
   CK(cudaSetDevice(h->device));
   const unsigned T = h->max_iter_kmeans;
-  if (h->harmony_slots.size() != 1) {  // harmony.cpp:214-228 cold start
-    TRY(run_assign(h, true));
-    CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));  // the cold start does not evaluate the objective
-  }
+  const bool cold = h->harmony_slots.size() != 1;  // harmony.cpp:214-228 cold start
   TRY(ensure_plan_rounds(h, (int)std::max(1u, T)));
   // the first persistent generation keeps its R-store rounds in a 32-bit mask: longer calls run the per-round path
   const bool persistent = h->use_v2 && !h->legacy_centroid && (h->use_v4 || T <= 31);
+  // The single-pass update kernel takes round 0's removal sums from the assignment step itself when that step
+  // runs in plan order (tensor-core kernel); every other combination runs the assignment in natural order first.
+  const bool plan_assign = cold && persistent && h->use_v4 && h->use_tc_assign && T > 0;
+  if (cold && !plan_assign) {
+    TRY(run_assign(h, true, false, false));  // the cold start does not evaluate the objective
+    CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
+  }
   if (update_orders && T > 0) {
     size_t cnt = (size_t)T * (size_t)h->N_global;
     if (h->perms_d.n < cnt) CK(h->perms_d.alloc(cnt));
@@ -1963,7 +2016,12 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
     } else {
       TRY(build_plans(h, (int)T, update_orders ? h->perms_d.p : nullptr, h->plan_set, h->stream));
     }
-    if (T > 0) TRY(upd_begin_call(h, (int)T));
+    if (T > 0) TRY(upd_begin_zero(h, (int)T));
+    if (plan_assign) {
+      TRY(run_assign(h, true, true, false));
+      CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));
+    }
+    if (T > 0) TRY(upd_begin_seed(h));
     unsigned t0 = 0;
     while (t0 < T) {
       unsigned t1 = (t0 == 0) ? std::min(T, h->window_size + 2) : t0 + 1;
@@ -1972,7 +2030,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
         if (t < 32 && (t == T - 1 || t > h->window_size)) mask |= 1u << t;  // rounds after which cluster_cpp may stop
       if (t0 > 0 && h->abort_cb && h->abort_cb(h->abort_user)) return -1;
       if (h->use_v4)
-        TRY(run_update_v4(h, (int)T, (int)t0, (int)t1));
+        TRY(run_update_v4(h, (int)T, (int)t0, (int)t1, plan_assign));
       else
         TRY(run_update_v2(h, (int)T, (int)t0, (int)t1, mask));
       iter = t1;
@@ -2026,6 +2084,7 @@ int hb_moe_correct_ridge(hb_handle* h) {
   if (!h->ran_init) return fail(h, 3, "init_cluster_cpp has not been run");
   CK(cudaSetDevice(h->device));
   TRY(run_correct(h));
+  h->zc_pending_norm = false;  // Z_corr was rebuilt from Z_orig
   if (h->C > 1) TRY(check_err_flag(h));
   return 0;
 }
@@ -2077,6 +2136,11 @@ int hb_get_field(hb_handle* h, int field, double* out) {
   switch (field) {
     case HB_Z_CORR: {
       HostLap lap(h->stream, "hb_get_field");
+      if (h->zc_pending_norm) {  // cluster_cpp leaves Z_corr cosine-normalised (harmony.cpp:220); done on first demand
+        k_normalise_rows<<<grid_for((int64_t)h->n * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->Zc.p, h->Zc.p, h->n, d, h->DS);
+        CKL();
+        h->zc_pending_norm = false;
+      }
       const int rc = download_rows(h, h->Zc.p, d, h->DS, out);
       lap.mark("Z_corr download");
       return rc;
@@ -2126,7 +2190,9 @@ int hb_set_field(hb_handle* h, int field, const double* in) {
   CK(cudaSetDevice(h->device));
   const int K = h->K, B = h->B, d = h->d;
   switch (field) {
-    case HB_Z_CORR: return upload_rows(h, in, d, h->DS, h->Zc.p);
+    case HB_Z_CORR:
+      h->zc_pending_norm = false;
+      return upload_rows(h, in, d, h->DS, h->Zc.p);
     case HB_R:
       h->R_user_set = true;
       return upload_rows(h, in, K, h->KS, h->R.p);

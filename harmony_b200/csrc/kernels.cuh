@@ -347,6 +347,26 @@ __global__ void k_assign_finalize(const float* __restrict__ O_acc, const float* 
   }
 }
 
+// Assignment step in plan order: the tiles' column sums went to the rem halves of the update kernel's accumulator
+// slots (slot(j) at (j + 1) * SL: [add | rem_O B*KS | rem_rs KS]); O = sum_j rem_O(j), E = (sum_j rem_rs(j)) Pr_b^T.
+__global__ void k_assign_finalize_plan(const float* __restrict__ acc, int nb, const float* __restrict__ Pr_b,
+                                       float* __restrict__ O, float* __restrict__ E, int B, int K, int KS) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < B * KS) {
+    const size_t XH = (size_t)B * KS + KS;
+    int b = idx / KS, k = idx - b * KS;
+    float o = 0.f, rs = 0.f;
+    if (k < K)
+      for (int j = 0; j < nb; ++j) {
+        const float* rem = acc + (size_t)(j + 1) * 2 * XH + XH;
+        o += rem[idx];
+        rs += rem[(size_t)B * KS + k];
+      }
+    O[idx] = o;
+    E[idx] = rs * Pr_b[b];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // update-order plan (replaces the physical shuffles of harmony.cpp:272-291)
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +564,25 @@ __global__ void k_plan_ranges(const int* __restrict__ seg_start, int nb, int J, 
     }
   }
   ranges[idx] = out;
+}
+// 128-row tiles of the (block, tuple) segments of a round (the assignment step in plan order)
+__global__ void k_plan_tilecount128(const int* __restrict__ seg_start, int S, int* __restrict__ tile_base) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x)
+    tile_base[s] = (s < S) ? (seg_start[s + 1] - seg_start[s] + 127) / 128 : 0;
+}
+__global__ void k_plan_tilefill128(const int* __restrict__ seg_start, const int* __restrict__ tile_base, int S, int J,
+                                   int* __restrict__ p0, int* __restrict__ len, int* __restrict__ tuple,
+                                   int* __restrict__ blk) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const int a = seg_start[s], e = seg_start[s + 1];
+    int i = tile_base[s];
+    for (int p = a; p < e; p += 128, ++i) {
+      p0[i] = p;
+      len[i] = min(128, e - p);
+      tuple[i] = s % J;
+      blk[i] = s / J;
+    }
+  }
 }
 __global__ void k_plan_tilecount(const int* __restrict__ seg_start, int S, int* __restrict__ tile_base) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x) {
