@@ -204,6 +204,16 @@ int my_ceil(float num) {
   return inum + 1;
 }
 
+// exchange area of the persistent update kernel for sharded cells (see setup_peer_exchange)
+struct XchArea {
+  int device = 0, world = 0, rank = 0;
+  size_t slots = 0, XH = 0, remT_floats = 0;
+  float* base = nullptr;     // [inbox: slots * world * XH floats | flags: slots * world words | remT: remT_floats]
+  void* peer[U4_MAXWORLD] = {};
+  unsigned epoch = 0;
+  bool leased = false;
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -282,6 +292,9 @@ struct hb_handle {
   bool use_v4 = false;   // single-pass persistent update kernel (update_kernel4.cuh): the default
   int u4_nbatch = 0;     // its ring size (batches of U4_BR rows)
   int plan_nsub = 1;     // third sort key of the plan: block in the next round (nb values) or off (1)
+  bool use_xch = false;  // sharded cells: block steps exchanged through peer memory (one cooperative launch per call)
+  Upd4Xch xch{};
+  XchArea* xarea = nullptr;  // leased exchange area (process-wide pool, see setup_peer_exchange)
   int assign_ns = 2;     // operand stages of the tensor-core assignment kernel
   bool zc_pending_norm = false;  // Zc holds the un-normalised corrected embedding although cluster_cpp has run
   DevBuf<int> pt_p0, pt_len, pt_tuple, pt_blk, pt_count, pt_base;  // [2 sets] 128-row tiles of round 0 in plan order
@@ -760,6 +773,123 @@ int run_update_R_v1(hb_handle* h, int t) {
   });
 }
 
+// ---- peer-memory exchange area of the persistent update kernel (sharded cells, one node) ----------------
+// Areas live for the life of the process, like the communicators: another rank may still be writing into an
+// area when its owner drops the handle, and unmapping needs a collective that a destructor cannot afford.  A
+// handle leases an area; areas are created collectively, so area i here is paired with area i of every rank.
+constexpr int XCH_MAX_AREAS = 16;
+std::vector<XchArea*> g_xch_areas;
+
+void release_peer_exchange(hb_handle* h) {
+  if (h->xarea) {
+    h->xarea->epoch = h->xch.epoch;  // the next lessee continues the epoch sequence
+    h->xarea->leased = false;
+    h->xarea = nullptr;
+  }
+  h->use_xch = false;
+}
+float* xch_inbox(const XchArea* a, void* base) { return reinterpret_cast<float*>(base); }
+unsigned* xch_flags(const XchArea* a, void* base) { return reinterpret_cast<unsigned*>(reinterpret_cast<float*>(base) + a->slots * a->world * a->XH); }
+float* xch_remT(const XchArea* a, void* base) {
+  return reinterpret_cast<float*>(base) + a->slots * a->world * a->XH + ((a->slots * a->world + 3) & ~(size_t)3);
+}
+// Collective over the handle's communicator.  Leases an area all ranks have free, or creates a new one:
+// allocates this rank's part, exchanges the IPC handles and maps the other ranks' parts.  If any rank cannot
+// map a peer the exchange stays off on all ranks (the update then runs one launch + all-reduce per block step).
+int setup_peer_exchange(hb_handle* h, int Tplan) {
+  const int W = h->world;
+  const size_t BK = (size_t)h->B * h->KS, XH = BK + h->KS;
+  const size_t slots = (size_t)Tplan * h->nb + 2;
+  const size_t remT_floats = 2 * (size_t)h->nb * h->J * h->KS;
+  release_peer_exchange(h);
+  // 1. agree on a reusable area: free here AND on every other rank, same shape
+  int64_t freev[XCH_MAX_AREAS + 2];
+  for (int i = 0; i < XCH_MAX_AREAS; ++i) {
+    const XchArea* a = i < (int)g_xch_areas.size() ? g_xch_areas[i] : nullptr;
+    freev[i] = (a && !a->leased && a->device == h->device && a->world == W && a->rank == h->rank && a->slots == slots &&
+                a->XH == XH && a->remT_floats == remT_floats) ? 1 : 0;
+  }
+  freev[XCH_MAX_AREAS] = (int64_t)g_xch_areas.size();       // min over ranks = smallest pool ...
+  freev[XCH_MAX_AREAS + 1] = -(int64_t)g_xch_areas.size();  // ... and -(largest pool): they must agree
+  DevBuf<int64_t> dv;
+  CK(dv.alloc(XCH_MAX_AREAS + 2));
+  CK(cudaMemcpyAsync(dv.p, freev, sizeof(freev), cudaMemcpyHostToDevice, h->stream));
+  CKN(g_nccl.AllReduce(dv.p, dv.p, XCH_MAX_AREAS + 2, ncclInt64, ncclMin, h->comm, h->stream));
+  CK(cudaMemcpyAsync(freev, dv.p, sizeof(freev), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  XchArea* area = nullptr;
+  for (int i = 0; i < XCH_MAX_AREAS && !area; ++i)
+    if (freev[i] == 1) area = g_xch_areas[i];
+  if (!area) {
+    // every rank sees the same reduced values, so every rank takes the same branch here
+    if (freev[XCH_MAX_AREAS] != -freev[XCH_MAX_AREAS + 1] || freev[XCH_MAX_AREAS] >= XCH_MAX_AREAS) return 0;  // out of step / pool full
+    // 2. create a new area (collective)
+    XchArea tmp;
+    tmp.slots = slots;
+    tmp.world = W;
+    tmp.XH = XH;
+    const size_t total = (size_t)(xch_remT(&tmp, nullptr) - (float*)nullptr) + remT_floats;
+    float* base = nullptr;
+    CK(cudaMalloc((void**)&base, sizeof(float) * total));
+    CK(cudaMemsetAsync(base, 0, sizeof(float) * total, h->stream));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, base));
+    DevBuf<char> ds, dr;
+    CK(ds.alloc(sizeof(mine)));
+    CK(dr.alloc(sizeof(mine) * W));
+    CK(cudaMemcpyAsync(ds.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllGather(ds.p, dr.p, sizeof(mine), ncclChar, h->comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    CK(cudaMemcpyAsync(all.data(), dr.p, sizeof(mine) * W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    area = new XchArea();
+    area->device = h->device;
+    area->world = W;
+    area->rank = h->rank;
+    area->slots = slots;
+    area->XH = XH;
+    area->remT_floats = remT_floats;
+    area->base = base;
+    int64_t ok = 1;
+    for (int r = 0; r < W; ++r) {
+      if (r == h->rank) continue;
+      if (cudaIpcOpenMemHandle(&area->peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        area->peer[r] = nullptr;
+        ok = 0;
+      }
+    }
+    CK(cudaMemcpyAsync(dv.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, h->stream));
+    CKN(g_nccl.AllReduce(dv.p, dv.p, 1, ncclInt64, ncclMin, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&ok, dv.p, sizeof(ok), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    area->leased = !ok;            // an unusable area keeps its index (the ranks stay in step) but is never leased
+    g_xch_areas.push_back(area);
+    if (!ok) {
+      h->warnings.push_back("peer-memory exchange unavailable (CUDA IPC mapping failed); using per-step all-reduce");
+      return 0;
+    }
+  }
+  area->leased = true;
+  h->xarea = area;
+  Upd4Xch& x = h->xch;
+  x.world = W;
+  x.rank = h->rank;
+  x.epoch = area->epoch;
+  x.XH = (int)XH;
+  for (int r = 0; r < W; ++r) {
+    void* b = (r == h->rank) ? (void*)area->base : area->peer[r];
+    x.peer_inbox[r] = xch_inbox(area, b);
+    x.peer_flags[r] = xch_flags(area, b);
+    x.peer_remT[r] = xch_remT(area, b);
+  }
+  x.inbox = x.peer_inbox[h->rank];
+  x.flags = x.peer_flags[h->rank];
+  h->use_xch = true;
+  return 0;
+}
+float* remT_ptr(hb_handle* h) { return h->use_xch ? h->xch.peer_remT[h->rank] : h->remT.p; }
+
 // ---- persistent update kernels over rounds [t0, t1) of this cluster_cpp call ---------------------------
 int nv_for(int KS) {
   int nv = 1;
@@ -829,7 +959,7 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.Pr_b = h->Pr_b.p;
   a.ring = h->ring.p;
   a.acc = h->acc2.p;
-  a.remT = h->remT.p;
+  a.remT = remT_ptr(h);
   a.OEend = h->OEend.p;
   a.obj = h->obj2.p;
   a.bar = h->bar.p;
@@ -858,7 +988,8 @@ int upd_begin_zero(hb_handle* h, int T) {
   CK(cudaMemsetAsync(h->acc2.p, 0, sizeof(float) * SL * ((size_t)T * h->nb + 2), h->stream));
   CK(cudaMemsetAsync(h->obj2.p, 0, sizeof(double) * 2 * (size_t)T, h->stream));
   CK(cudaMemsetAsync(h->bar.p, 0, sizeof(unsigned) * 2 * ((size_t)T * h->nb + 2), h->stream));
-  if (h->use_v4) CK(cudaMemsetAsync(h->remT.p, 0, sizeof(float) * h->remT.n, h->stream));
+  if (h->use_v4) CK(cudaMemsetAsync(remT_ptr(h), 0, sizeof(float) * 2 * (size_t)h->nb * h->J * h->KS, h->stream));
+  if (h->use_xch) h->xch.epoch++;  // flags of earlier calls no longer match
   return 0;
 }
 // ... and seed ring[1] (= "O_{-1}") with the tables the call starts from
@@ -889,12 +1020,15 @@ int upd4_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
   const size_t smem = upd4_smem_bytes(NV, a.nbatch, a.KS);
   CK(cudaFuncSetAttribute(k_update_steps4<NV, SIGU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.coop = cooperative ? 1 : 0;
+  Upd4Launch lp;
+  lp.a = a;
+  if (h->use_xch) lp.x = h->xch;
   if (cooperative) {
-    void* args[] = {&a};
+    void* args[] = {&lp};
     CK(cudaLaunchCooperativeKernel((void*)k_update_steps4<NV, SIGU>, dim3(h->coop_grid), dim3(U4_THREADS), args, smem,
                                    h->stream));
   } else {
-    k_update_steps4<NV, SIGU><<<h->coop_grid, U4_THREADS, smem, h->stream>>>(a);
+    k_update_steps4<NV, SIGU><<<h->coop_grid, U4_THREADS, smem, h->stream>>>(lp);
   }
   CKL();
   return 0;
@@ -947,13 +1081,13 @@ int run_update_v4(hb_handle* h, int T, int t0, int t1, bool rem_ready) {
     if (h->world > 1)
       for (int j = 0; j < nb; ++j) TRY(allreduce_f(h, h->acc2.p + (size_t)(j + 1) * SL + XH, XH));
   }
-  if (h->world <= 1) {
+  if (h->world <= 1 || h->use_xch) {
     a.s_begin = t0 * nb;
     a.s_end = t1 * nb;
     RegionScope r3(h, "k_update_steps");
     TRY(upd4_launch(h, a, true));
   } else {
-    // sharded cells: one launch per block step, the step's add half all-reduced in between; the next round's
+    // sharded cells without peer memory: one launch per block step, the step's add half all-reduced in between; the next round's
     // removal sums (remT) are all-reduced and folded once per round
     RegionScope r3(h, "k_update_steps");
     for (int t = t0; t < t1; ++t) {
@@ -974,7 +1108,7 @@ int run_update_v4(hb_handle* h, int T, int t0, int t1, bool rem_ready) {
   if (h->dbg_cta >= 0 && h->world <= 1) dump_step_trace(h, (t1 - t0) * nb, 8);
   {
     RegionScope r4(h, "k_update_finalize");
-    k_update_finalize4<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, t1 * nb, h->O.p, h->E.p);
+    k_update_finalize4<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, h->use_xch ? h->xch : Upd4Xch{}, t1 * nb, h->O.p, h->E.p);
     CKL();
   }
   return push_round_objectives(h, t0, t1);
@@ -1363,6 +1497,7 @@ void hb_destroy(hb_handle* h) {
   if (h->plan_done) cudaEventDestroy(h->plan_done);
   if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
+  release_peer_exchange(h);
   cudaStream_t s = h->stream;
   delete h;  // frees device buffers
   if (s) cudaStreamDestroy(s);
@@ -1736,6 +1871,9 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->obj2.alloc(2 * (size_t)Tplan));
     CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));
     if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)Tplan * h->nb * h->coop_grid));
+    release_peer_exchange(h);
+    if (h->use_v4 && h->world > 1 && h->world <= U4_MAXWORLD && getenv("HB_NO_PEER_EXCHANGE") == nullptr)
+      TRY(setup_peer_exchange(h, Tplan));
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
       CK(h->dbg.alloc((size_t)(32 * h->nb + 2) * 16));
@@ -1949,6 +2087,7 @@ int ensure_plan_rounds(hb_handle* h, int T) {
     CK(h->obj2.alloc(2 * (size_t)T));
     CK(h->bar.alloc(2 * ((size_t)T * h->nb + 2)));
     if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)T * h->nb * h->coop_grid));
+    if (h->use_xch) TRY(setup_peer_exchange(h, T));  // collective: every rank grows its plan in the same call
   }
   h->plan_rounds = T;
   return 0;

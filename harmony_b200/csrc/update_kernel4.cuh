@@ -74,6 +74,45 @@ struct Upd4Args {
   long long* dbg;        // optional [steps][8] globaltimer stamps of CTA dbg_cta (null = off)
   int dbg_cta;
 };
+// Sharded cells on one node (one process per GPU): the per-step sums cross GPUs through peer memory instead of a
+// collective per block step.  Every rank owns an exchange area that all ranks of the node have mapped (CUDA IPC
+// over NVLink):  inbox[slot][src][XH]  (XH = B KS + KS floats: the add half of an accumulator slot),
+// flags[slot][src], and the rank's remT tables.  The CTA that completes the LOCAL add half of a slot copies it into
+// entry src = rank of every rank's inbox and then raises the flags (value = epoch of the running cluster_cpp call);
+// readers wait for the `world` flags of a slot and add the entries in rank order, so every rank derives bit-identical
+// tables.  The next round's removal sums are read from the peers' remT directly when a round is folded.
+constexpr int U4_MAXWORLD = 8;
+struct Upd4Xch {
+  int world = 1, rank = 0;
+  unsigned epoch = 0;
+  int XH = 0;
+  float* inbox = nullptr;       // local area
+  unsigned* flags = nullptr;
+  float* peer_inbox[U4_MAXWORLD] = {};
+  unsigned* peer_flags[U4_MAXWORLD] = {};
+  float* peer_remT[U4_MAXWORLD] = {};  // every rank's remT (own entry = local pointer)
+};
+
+__device__ __forceinline__ unsigned u4_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void u4_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// sum over the ranks' entries of element `off` of the add half of accumulator slot index `sl`, in rank order
+__device__ __forceinline__ float u4_xsum(const Upd4Xch& x, int sl, int off) {
+  const float* q = x.inbox + ((size_t)sl * x.world) * x.XH + off;
+  float t = 0.f;
+  for (int r = 0; r < x.world; ++r) t += __ldcg(q + (size_t)r * x.XH);
+  return t;
+}
+
+struct Upd4Launch {
+  Upd4Args a;
+  Upd4Xch x;
+};
 
 __device__ __forceinline__ unsigned u4_ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -137,9 +176,10 @@ struct U4Tables {
   const float* cur;     // slot(s)
   int BK, KS;
 };
-// O_s, E_s and P_s of element (b, k); every input was completed before the counter this CTA waited for
+// O_s, E_s and P_s of element (b, k); every input was completed before the counter this CTA waited for.
+// xs >= 0: sharded cells, the add half of slot index xs is the sum of the ranks' inbox entries (xs < 0: local / none)
 __device__ __forceinline__ void u4_derive(const U4Tables& tv, const float* Pr_b, const float* theta, int b, int k, float& o,
-                                          float& e, float& p) {
+                                          float& e, float& p, const Upd4Xch* x = nullptr, int xs = -1) {
   const int idx = b * tv.KS + k;
   const float prb = __ldg(Pr_b + b);
   const float* prev_rem_O = tv.prev + tv.BK + tv.KS;
@@ -148,8 +188,16 @@ __device__ __forceinline__ void u4_derive(const U4Tables& tv, const float* Pr_b,
   const float* cur_add_rs = tv.cur + tv.BK;
   const float* cur_rem_O = tv.cur + tv.BK + tv.KS;
   const float* cur_rem_rs = cur_rem_O + tv.BK;
-  o = (__ldcg(tv.ringO + idx) - __ldcg(prev_rem_O + idx)) + __ldcg(cur_add_O + idx);
-  e = (__ldcg(tv.ringE + idx) - __ldcg(prev_rem_rs + k) * prb) + __ldcg(cur_add_rs + k) * prb;
+  float add_o, add_rs;
+  if (x) {
+    add_o = (xs >= 0) ? u4_xsum(*x, xs, idx) : 0.f;
+    add_rs = (xs >= 0) ? u4_xsum(*x, xs, tv.BK + k) : 0.f;
+  } else {
+    add_o = __ldcg(cur_add_O + idx);
+    add_rs = __ldcg(cur_add_rs + k);
+  }
+  o = (__ldcg(tv.ringO + idx) - __ldcg(prev_rem_O + idx)) + add_o;
+  e = (__ldcg(tv.ringE + idx) - __ldcg(prev_rem_rs + k) * prb) + add_rs * prb;
   const float e_eff = e - __ldcg(cur_rem_rs + k) * prb;
   const float o_eff = o - __ldcg(cur_rem_O + idx);
   p = u4_penalty_pow(o_eff, e_eff, __ldg(theta + b));
@@ -179,8 +227,11 @@ inline int upd4_nbatch(int KS, size_t limit) {
 }
 
 template <int NV, bool SIGU>
-__global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
+__global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Launch lp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Upd4Args& a = lp.a;
+  const Upd4Xch& x = lp.x;
+  const bool multi = x.world > 1;  // sharded cells with the peer-memory exchange
   constexpr int KP4 = 128 * NV;
   constexpr int RU = (NV <= 2) ? 2 : 1;  // rows in flight per consumer warp
   const int K = a.K, KS = a.KS, C = a.C, J = a.J, B = a.B, nb = a.nb;
@@ -201,6 +252,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
   int* consumed = nxt + (size_t)NBT * U4_BR;                // rows handed back per slot, cumulative
   int* issued_w = consumed + NBT;                           // batches issued per producer warp, cumulative
   __shared__ double sh_obj[2];
+  __shared__ int sh_last;
 
   // stale ring rows are read (with weight 0) by the tail of a row group: they must be finite
   for (float* q = ringbuf + tid; q < ringbuf + (size_t)NBT * U4_BR * KS; q += U4_THREADS) *q = 0.f;
@@ -302,16 +354,49 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) lane_ok[v] = (lane + 32 * v) < KS4;
 
-  auto signal = [&](unsigned* c) {
+  // signal(c, sl): this CTA is done with the step counted by c.  Sharded cells: the CTA that completes the count
+  // publishes the finished add half of accumulator slot index sl to every rank (sl < 0: nothing to publish).
+  auto signal = [&](unsigned* c, int sl) {
     u4_gsync();
+    if (!multi || sl < 0) {
+      if (gt == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+      }
+      return;
+    }
     if (gt == 0) {
       __threadfence();
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+      const unsigned old = atomicAdd(c, 1u);
+      __threadfence();
+      sh_last = (old == (unsigned)grid - 1u) ? 1 : 0;
+    }
+    u4_gsync();
+    if (sh_last) {
+      const float* src = a.acc + (size_t)sl * SL;  // complete: every CTA's atomics preceded its count
+      const size_t entry = (size_t)sl * x.world + x.rank;
+      for (int r = 0; r < x.world; ++r) {
+        float* dst = x.peer_inbox[r] + entry * x.XH;
+        for (int i = gt * 4; i < x.XH; i += U4_GT * 4)
+          *reinterpret_cast<float4*>(dst + i) = __ldcg(reinterpret_cast<const float4*>(src + i));
+      }
+      __threadfence_system();
+      u4_gsync();
+      if (gt < x.world) u4_st_release_sys(x.peer_flags[gt] + entry, x.epoch);
     }
   };
   auto wait_for = [&](const unsigned* c) {
     if (gt == 0) {
       while (u4_ld_acquire_gpu(c) < (unsigned)grid) __nanosleep(20);
+      __threadfence();
+    }
+    u4_gsync();
+  };
+  // sharded cells: every rank's entry of the add half of slot index sl has arrived in the local inbox
+  auto wait_slot = [&](int sl) {
+    if (gt < x.world) {
+      const unsigned* f = x.flags + (size_t)sl * x.world + gt;
+      while (u4_ld_acquire_sys(f) != x.epoch) __nanosleep(40);
       __threadfence();
     }
     u4_gsync();
@@ -334,27 +419,35 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
     tv.KS = KS;
     return tv;
   };
-  // removal sums of round t: remT[t & 1][j][q][:] (filed during round t-1) -> rem halves of slot(t nb + j); each
-  // (j, k) column is owned by one thread of the grid, which also clears the table for round t+2
+  // removal sums of round t: remT[t & 1][j][q][:] (filed during round t-1; sharded cells: summed over the ranks'
+  // tables in rank order) -> rem halves of slot(t nb + j); each (j, k) column is owned by one thread of the grid, which
+  // also clears the other parity for round t (every rank has read it: all of them have finished round t-1)
   auto fold_round = [&](int t) {
-    float* T0 = a.remT + (size_t)(t & 1) * nb * J * KS;
+    const size_t par_off = (size_t)(t & 1) * nb * J * KS;
+    float* Tz = a.remT + (size_t)((t + 1) & 1) * nb * J * KS;
     for (int item = cta * U4_GT + gt; item < nb * K; item += grid * U4_GT) {
       const int j = item / K, k = item - j * K;
-      float* Tj = T0 + (size_t)j * J * KS;
+      const size_t joff = par_off + (size_t)j * J * KS + k;
       float* slot = a.acc + (size_t)(t * nb + j + 1) * SL;
       float* rem_O = slot + BK + KS;
       float* rem_rs = rem_O + BK;
       float rs = 0.f;
       for (int q = 0; q < J; ++q) {
-        const float v = __ldcg(Tj + (size_t)q * KS + k);
+        float v;
+        if (multi) {
+          v = 0.f;
+          for (int r = 0; r < x.world; ++r) v += __ldcg(x.peer_remT[r] + joff + (size_t)q * KS);
+        } else {
+          v = __ldcg(a.remT + joff + (size_t)q * KS);
+        }
         if (v != 0.f) {
           rs += v;
           for (int c = 0; c < C; ++c) {
             float* o = rem_O + (size_t)__ldg(a.tuple_levels + q * C + c) * KS + k;
             *o = *o + v;
           }
-          Tj[(size_t)q * KS + k] = 0.f;
         }
+        Tz[((size_t)j * J + q) * KS + k] = 0.f;
       }
       rem_rs[k] = rs;
     }
@@ -391,12 +484,15 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
     const bool has_next = t < a.has_next_from;
     if (a.coop) {
       if (s > a.s_begin) wait_for(cntU + s - 1);  // add_{s-1}, ring(s-1); at j == 0 also: round t-1 is complete
+      if (multi && s >= 1) wait_slot(s + 1);      // ... on every rank: add_{s-1} lives in slot(s) = index s + 1
       if (j == 0 && t > 0) {
         fold_round(t);
-        signal(cntF + t);
+        signal(cntF + t, -1);
         wait_for(cntF + t);
       }
     }
+    const Upd4Xch* xp = multi ? &x : nullptr;
+    const int xs = (s >= 1) ? s + 1 : -1;
     stamp(s, 1);
     // ---- tables of the step: the penalty row of this CTA's tuple, and this CTA's share of O_s, E_s ----
     {
@@ -406,7 +502,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
           float v = 0.f;
           for (int c = 0; c < C; ++c) {
             float o, e, pp;
-            u4_derive(tv, a.Pr_b, a.theta, __ldg(a.tuple_levels + q * C + c), k, o, e, pp);
+            u4_derive(tv, a.Pr_b, a.theta, __ldg(a.tuple_levels + q * C + c), k, o, e, pp, xp, xs);
             v += pp;
           }
           tab[k] = v;
@@ -418,7 +514,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
       for (int idx = cta + grid * (U4_GT - 1 - gt); idx < BK; idx += grid * U4_GT) {  // the last threads first: they idle above
         const int b = idx / KS, k = idx - b * KS;
         float o = 0.f, e = 0.f, pp = 0.f;
-        if (k < K) u4_derive(tv, a.Pr_b, a.theta, b, k, o, e, pp);
+        if (k < K) u4_derive(tv, a.Pr_b, a.theta, b, k, o, e, pp, xp, xs);
         outO[idx] = o;
         outE[idx] = e;
         if (j == 0 && t > 0) {
@@ -598,7 +694,7 @@ __global__ void __launch_bounds__(U4_THREADS, 1) k_update_steps4(Upd4Args a) {
     }
     if ((s + 1) % nb == 0) flush_objective(t);
     stamp(s, 6);
-    if (a.coop) signal(cntU + s);
+    if (a.coop) signal(cntU + s, s + 2);  // add_s lives in slot(s + 1) = index s + 2
     gb0 += nbt;
   }
   if (a.s_end % nb != 0 && a.s_end > a.s_begin) flush_objective((a.s_end - 1) / nb);  // partial round
@@ -647,29 +743,38 @@ __global__ void __launch_bounds__(256) k_rem_sums(const float* __restrict__ R, c
 __global__ void k_fold_round(Upd4Args a, int t) {
   const int K = a.K, KS = a.KS, C = a.C, J = a.J, nb = a.nb;
   const int BK = a.B * KS, SL = 2 * (BK + KS);
-  float* T0 = a.remT + (size_t)(t & 1) * nb * J * KS;
+  const float* T0 = a.remT + (size_t)(t & 1) * nb * J * KS;
+  float* Tz = a.remT + (size_t)((t + 1) & 1) * nb * J * KS;
   for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < nb * K; item += gridDim.x * blockDim.x) {
     const int j = item / K, k = item - j * K;
-    float* Tj = T0 + (size_t)j * J * KS;
     float* slot = a.acc + (size_t)(t * nb + j + 1) * SL;
     float* rem_O = slot + BK + KS;
     float* rem_rs = rem_O + BK;
     float rs = 0.f;
     for (int q = 0; q < J; ++q) {
-      const float v = Tj[(size_t)q * KS + k];
+      const float v = T0[((size_t)j * J + q) * KS + k];
       if (v != 0.f) {
         rs += v;
         for (int c = 0; c < C; ++c) rem_O[(size_t)a.tuple_levels[q * C + c] * KS + k] += v;
-        Tj[(size_t)q * KS + k] = 0.f;
       }
+      Tz[((size_t)j * J + q) * KS + k] = 0.f;
     }
     rem_rs[k] = rs;
   }
 }
 
 // After the last executed step S: O = O_S, E = E_S into the handle's tables.
-__global__ void k_update_finalize4(Upd4Args a, int S, float* __restrict__ O, float* __restrict__ E) {
+__global__ void k_update_finalize4(Upd4Args a, Upd4Xch x, int S, float* __restrict__ O, float* __restrict__ E) {
   const int KS = a.KS, BK = a.B * KS, SL = 2 * (BK + KS);
+  const bool multi = x.world > 1;
+  if (multi && S >= 1) {  // the other ranks' kernels may still be running: wait for their last add halves
+    if ((int)threadIdx.x < x.world) {
+      const unsigned* f = x.flags + (size_t)(S + 1) * x.world + threadIdx.x;
+      while (u4_ld_acquire_sys(f) != x.epoch) __nanosleep(40);
+      __threadfence();
+    }
+    __syncthreads();
+  }
   const float* ringO = a.ring + (size_t)((S - 1) & 1) * 2 * BK;
   const float* ringE = ringO + BK;
   const float* prev = a.acc + (size_t)(S)*SL;
@@ -682,8 +787,10 @@ __global__ void k_update_finalize4(Upd4Args a, int S, float* __restrict__ O, flo
       const float prb = a.Pr_b[b];
       const float* prev_rem_O = prev + BK + KS;
       const float* prev_rem_rs = prev_rem_O + BK;
-      o = (ringO[idx] - prev_rem_O[idx]) + cur[idx];
-      e = (ringE[idx] - prev_rem_rs[k] * prb) + cur[BK + k] * prb;
+      const float add_o = multi ? (S >= 1 ? u4_xsum(x, S + 1, idx) : 0.f) : cur[idx];
+      const float add_rs = multi ? (S >= 1 ? u4_xsum(x, S + 1, BK + k) : 0.f) : cur[BK + k];
+      o = (ringO[idx] - prev_rem_O[idx]) + add_o;
+      e = (ringE[idx] - prev_rem_rs[k] * prb) + add_rs * prb;
     }
     O[idx] = o;
     E[idx] = e;
