@@ -56,6 +56,7 @@ struct Assign3Args {
   int ns;         // operand stages (1 or 2)
   int normalise;  // divide by the row norm (cold start; init runs on rows that setup normalised)
   int want_obj;   // objective partial sums (init)
+  long long* dbg; // optional [32 tiles][16] globaltimer stamps of CTA 0 (null = off)
 };
 
 __host__ __device__ inline int assign3_stage_stride(int KS) { return ((KS >> 2) | 1) << 2; }
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
   for (int i = tid; i < NS * TC_TM * KD; i += A3_THREADS) Ahi[i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(raw_full + i, 33);
+      umma::mbar_init(raw_full + i, 1);  // (unused)
       umma::mbar_init(lo_full + i, 128);
       umma::mbar_init(st_empty + i, 1);
     }
@@ -133,52 +134,16 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
 
   const int my_first = blockIdx.x, stride = gridDim.x;
   if (a.ntiles_ptr) a.ntiles = __ldg(a.ntiles_ptr);
+  auto stamp = [&](int it, int slot) {
+    if (a.dbg && blockIdx.x == 0 && it < 32) {
+      long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      a.dbg[it * 16 + slot] = tns;
+    }
+  };
 
   if (warp == 0) {
-    // =============================== gather producer ===============================
-    // lane -> (row of a pair, 16-byte chunk): lanes 0 .. DS4-1 carry row 2i, the next DS4 lanes row 2i + 1 when
-    // 2 DS4 <= 32, else one row per instruction and several passes over the chunks
-    const bool two = 2 * DS4 <= 32;
-    const int sub = two ? (lane >= DS4 ? 1 : 0) : 0;
-    const int ch0 = two ? (lane - sub * DS4) : lane;
-    const bool on = two ? (lane < 2 * DS4) : true;
-    const int rows_per = two ? 2 : 1;
-    int it = 0;
-    for (int tile = my_first; tile < a.ntiles; tile += stride, ++it) {
-      const int s = it % NS, use = it / NS;
-      const int p0 = __ldg(a.tile_p0 + tile), len = __ldg(a.tile_len + tile);
-      int* rc = rowcell + (size_t)(it % A3_RING_C) * TC_TM;
-      // row -> cell of the tile (4 rows per lane); in flight while the stage drains
-      int cells[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = lane + 32 * i;
-        cells[i] = (r < len) ? (a.row_index ? __ldg(a.row_index + p0 + r) : p0 + r) : 0;
-      }
-      if (use >= 1) umma::mbar_wait(st_empty + s, (use - 1) & 1);
-      float* dst = Ahi + (size_t)s * TC_TM * KD;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        rc[lane + 32 * i] = cells[i];
-        if (32 * i < len) {
-          for (int rr = 0; rr < 32; rr += rows_per) {
-            const int cell = __shfl_sync(0xffffffffu, cells[i], (rr + sub) & 31);
-            const int r = 32 * i + rr + sub;
-            if (on && r < len) {
-              const float* src = a.Zc + (size_t)cell * DS;
-              for (int c = ch0; c < DS4; c += 32) {
-                const unsigned sp = umma::smem_u32(dst + ((size_t)c * TC_TM + r) * 4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sp), "l"(src + 4 * c) : "memory");
-              }
-            }
-          }
-        }
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(raw_full + s)) : "memory");
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(raw_full + s);  // releases the row -> cell words
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    // (spare warp: the row gather is done by the converter threads, one row each)
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
@@ -189,7 +154,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
       for (int tile = my_first; tile < a.ntiles; tile += stride, ++it) {
         const int s = it % NS, acc = it & 1;
         umma::mbar_wait(lo_full + s, (it / NS) & 1);
+        stamp(it, 5);
         if (it >= 2) umma::mbar_wait(t_empty + acc, ((it >> 1) - 1) & 1);
+        stamp(it, 6);
         umma::fence_after_sync();
         const uint32_t aH = umma::smem_u32(Ahi + (size_t)s * TC_TM * KD);
         const uint32_t aL = umma::smem_u32(Alo + (size_t)s * TC_TM * KD);
@@ -207,20 +174,68 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
         }
         umma::mma_commit(st_empty + s);   // operands consumed -> the producer may refill the stage
         umma::mma_commit(t_full + acc);   // accumulator ready
+        stamp(it, 7);
       }
     }
   } else if (warp < 6) {
-    // =============================== converters: lo tile + row norms ===============================
+    // =============================== row loaders + converters (one row of the tile per thread) ===============================
+    // Thread r copies ITS row of the next tile with 16-byte cp.async straight into the canonical K-major operand
+    // layout (consecutive lanes -> consecutive 16-byte slots of a chunk plane: conflict-free; one warp-wide gather
+    // instruction with scattered destinations costs ~290 cycles of a single producer warp, measured), waits for its
+    // own copies of the current tile (cp.async.wait_group: no mbarrier between loading and converting), produces the
+    // `lo` operand and the row norm, and hands the stage to the MMA issuer.  Plan entries run two tiles ahead.
     const int r = tid - 64;  // row of the tile
+    auto tile_of = [&](int it) { return my_first + it * stride; };
+    auto ld_meta = [&](int it, int& p0, int& len) {
+      const int tile = tile_of(it);
+      p0 = 0;
+      len = 0;
+      if (tile < a.ntiles) {
+        p0 = __ldg(a.tile_p0 + tile);
+        len = __ldg(a.tile_len + tile);
+      }
+    };
+    auto ld_cell = [&](int p0, int len) { return (r < len) ? (a.row_index ? __ldg(a.row_index + p0 + r) : p0 + r) : -1; };
+    auto issue_row = [&](int it, int cell) {  // tile `it` -> stage it % NS; always commits
+      if (cell >= 0) {
+        const int s = it % NS;
+        const float* src = a.Zc + (size_t)cell * DS;
+        const unsigned dst = umma::smem_u32(Ahi + (size_t)s * TC_TM * KD + (size_t)r * 4);
+        for (int c = 0; c < DS4; ++c)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)c * (TC_TM * 16u)), "l"(src + 4 * c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int p0_0, len0, p0_1, len1, p0_2, len2;
+    ld_meta(0, p0_0, len0);
+    ld_meta(1, p0_1, len1);
+    ld_meta(2, p0_2, len2);
+    int cell0 = ld_cell(p0_0, len0), cell1 = ld_cell(p0_1, len1);
+    issue_row(0, cell0);
     int it = 0;
     for (int tile = my_first; tile < a.ntiles; tile += stride, ++it) {
       const int s = it % NS;
-      const int len = __ldg(a.tile_len + tile);
-      umma::mbar_wait(raw_full + s, (it / NS) & 1);
+      if (r == 0) stamp(it, 0);
+      // next tile -> the other stage (with one stage: after this tile's MMAs, below)
+      if (NS == 2) {
+        if (it >= 1 && tile + stride < a.ntiles) umma::mbar_wait(st_empty + ((it + 1) & 1), ((it - 1) >> 1) & 1);  // MMAs of tile it - 1
+        if (r == 0) stamp(it, 1);
+        issue_row(it + 1, cell1);
+        if (r == 0) stamp(it, 2);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      rowcell[(size_t)(it % A3_RING_C) * TC_TM + r] = cell0 >= 0 ? cell0 : 0;
+      // plan entries two / three tiles ahead
+      const int cell2 = ld_cell(p0_2, len2);
+      int p0_3, len3;
+      ld_meta(it + 3, p0_3, len3);
+      if (r == 0) stamp(it, 3);
       const float* hi = Ahi + (size_t)s * TC_TM * KD;
       float* lo = Alo + (size_t)s * TC_TM * KD;
       float ss = 0.f;
-      const bool live = r < len;
+      const bool live = cell0 >= 0;
       for (int c = 0; c < KD4; ++c) {
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f), l4 = z;
         if (live && c < DS4) {
@@ -242,8 +257,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
       }
       rnorm[(size_t)(it % A3_RING_N) * TC_TM + r] = live ? rn : 0.f;  // rows beyond the tile: cos = 0, finite exp
       if (a.Zc_out && a.normalise && live) {  // compatibility paths read the normalised embedding back
-        const int cell = rowcell[(size_t)(it % A3_RING_C) * TC_TM + r];
-        float4* zw = reinterpret_cast<float4*>(a.Zc_out + (size_t)cell * DS);
+        float4* zw = reinterpret_cast<float4*>(a.Zc_out + (size_t)cell0 * DS);
         for (int c = 0; c < DS4; ++c) {
           float4 z = *reinterpret_cast<const float4*>(hi + ((size_t)c * TC_TM + r) * 4);
           z.x *= rn;
@@ -253,9 +267,19 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
           zw[c] = z;
         }
       }
-      umma::fence_proxy_async();  // generic-proxy writes (lo) and the observed cp.async rows -> tensor core
+      umma::fence_proxy_async();  // this thread's cp.async rows (observed above) and `lo` writes -> tensor core
       umma::mbar_arrive(lo_full + s);
+      if (r == 0) stamp(it, 4);
+      if (NS == 1) {  // single stage: the next tile's rows can only land once this tile's MMAs are done
+        if (tile + stride < a.ntiles) umma::mbar_wait(st_empty, it & 1);
+        issue_row(it + 1, cell1);
+      }
+      cell0 = cell1;
+      cell1 = cell2;
+      p0_2 = p0_3;
+      len2 = len3;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
     // =============================== epilogue ===============================
     const int ew = warp - 6;           // 0..7
@@ -275,6 +299,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
       const bool live = r < len;
       umma::mbar_wait(t_full + acc, (it >> 1) & 1);
       umma::fence_after_sync();
+      if (et == 0) stamp(it, 8);
       const float rn = rnorm[(size_t)(it % A3_RING_N) * TC_TM + r];
       const uint32_t trow = tmem + acc * 128 + ((uint32_t)(q * 32) << 16);
       float ev[64];                        // exp(u) of this thread's columns
@@ -313,7 +338,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
       // TMEM accumulator fully read -> the issuer may overwrite it
       umma::fence_before_sync();
       umma::mbar_arrive(t_empty + acc);
+      if (et == 0) stamp(it, 9);
       umma::named_sync(1, 256);
+      if (et == 0) stamp(it, 10);
       // R.each_row() /= sum(R, 0) (no zero guard in the reference); rows beyond the tile weigh 0
       const float tot = rs_part[r] + rs_part[TC_TM + r];
       const float inv = live ? 1.f / tot : 0.f;
@@ -369,29 +396,65 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
           if ((lane & 1) == 0) cs_part[q * NP + c + bcol] = w1;
         }
       }
+      if (et == 0) stamp(it, 11);
       // rows out: the staged U tile (and, natural mode, R = exp(U) / row sum) with coalesced row stores
       {
         const int* rc = rowcell + (size_t)(it % A3_RING_C) * TC_TM;
-        for (int rr2 = ew; rr2 < len; rr2 += 8) {
-          const int cell = rc[rr2];
-          const float* us = Ust + (size_t)rr2 * SS;
-          float invr = 0.f;
-          if (a.R) invr = 1.f / (rs_part[rr2] + rs_part[TC_TM + rr2]);
-          for (int c4 = lane; c4 < KS4; c4 += 32) {
-            const float4 u4 = *reinterpret_cast<const float4*>(us + 4 * c4);
-            *reinterpret_cast<float4*>(a.U + (size_t)cell * KS + 4 * c4) = u4;
-            if (a.R) {
-              float4 r4;
-              r4.x = fast_exp(u4.x) * invr;
-              r4.y = fast_exp(u4.y) * invr;
-              r4.z = fast_exp(u4.z) * invr;
-              r4.w = fast_exp(u4.w) * invr;
-              *reinterpret_cast<float4*>(a.R + (size_t)cell * KS + 4 * c4) = r4;
+        const bool one = KS4 <= 32;  // one 16-byte piece per lane and row: four rows in flight per warp
+        if (one) {
+          const bool on = lane < KS4;
+          for (int rb = ew; rb < len; rb += 32) {
+            int cellv[4];
+            float4 u4[4];
+            float invr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr2 = rb + 8 * k;
+              const int rq = rr2 < len ? rr2 : rb;
+              cellv[k] = rc[rq];
+              u4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (on) u4[k] = *reinterpret_cast<const float4*>(Ust + (size_t)rq * SS + 4 * lane);
+              invr[k] = a.R ? 1.f / (rs_part[rq] + rs_part[TC_TM + rq]) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (on && rb + 8 * k < len) {
+                *reinterpret_cast<float4*>(a.U + (size_t)cellv[k] * KS + 4 * lane) = u4[k];
+                if (a.R) {
+                  float4 r4;
+                  r4.x = fast_exp(u4[k].x) * invr[k];
+                  r4.y = fast_exp(u4[k].y) * invr[k];
+                  r4.z = fast_exp(u4[k].z) * invr[k];
+                  r4.w = fast_exp(u4[k].w) * invr[k];
+                  *reinterpret_cast<float4*>(a.R + (size_t)cellv[k] * KS + 4 * lane) = r4;
+                }
+              }
+            }
+          }
+        } else {
+          for (int rr2 = ew; rr2 < len; rr2 += 8) {
+            const int cell = rc[rr2];
+            const float* us = Ust + (size_t)rr2 * SS;
+            float invr = 0.f;
+            if (a.R) invr = 1.f / (rs_part[rr2] + rs_part[TC_TM + rr2]);
+            for (int c4 = lane; c4 < KS4; c4 += 32) {
+              const float4 u4 = *reinterpret_cast<const float4*>(us + 4 * c4);
+              *reinterpret_cast<float4*>(a.U + (size_t)cell * KS + 4 * c4) = u4;
+              if (a.R) {
+                float4 r4;
+                r4.x = fast_exp(u4.x) * invr;
+                r4.y = fast_exp(u4.y) * invr;
+                r4.z = fast_exp(u4.z) * invr;
+                r4.w = fast_exp(u4.w) * invr;
+                *reinterpret_cast<float4*>(a.R + (size_t)cell * KS + 4 * c4) = r4;
+              }
             }
           }
         }
       }
+      if (et == 0) stamp(it, 12);
       umma::named_sync(1, 256);
+      if (et == 0) stamp(it, 13);
       // column sums of the tile -> the block's removal sums (plan mode) or O / row sums (natural mode)
       if (et < K) {
         const float t = (cs_part[et] + cs_part[NP + et]) + (cs_part[2 * NP + et] + cs_part[3 * NP + et]);

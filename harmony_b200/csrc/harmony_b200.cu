@@ -29,6 +29,7 @@
 #include "kernels.cuh"
 #include "update_kernel.cuh"
 #include "update_kernel4.cuh"
+#include "update_kernel5.cuh"
 #include "assign_tc3.cuh"
 #include "apply_tc.cuh"
 #include "apply_tc2.cuh"
@@ -291,6 +292,9 @@ struct hb_handle {
   DevBuf<double> objkeep;
   bool use_v4 = false;   // single-pass persistent update kernel (update_kernel4.cuh): the default
   int u4_nbatch = 0;     // its ring size (batches of U4_BR rows)
+  int u5_ring_rows = 0;  // rows of a warp's private ring (update_kernel5.cuh); 0: that kernel cannot run this row width
+  bool use_v5 = false;
+  int plan_batch = 1;    // rounds sorted per launch (size of the histogram scratch)
   int plan_nsub = 1;     // third sort key of the plan: block in the next round (nb values) or off (1)
   bool use_xch = false;  // sharded cells: block steps exchanged through peer memory (one cooperative launch per call)
   Upd4Xch xch{};
@@ -504,6 +508,14 @@ int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_o
       grid_tc = std::max(1, std::min(h->tc_ntiles, h->num_sms));
     }
     const size_t smem_tc = assign3_smem_bytes(t.ns, t.KD, t.NP, KS);
+    t.dbg = nullptr;
+    static int as_calls = 0;
+    const bool tracing = getenv("HB_TRACE_ASSIGN") != nullptr && plan_mode && (++as_calls == 4);
+    if (tracing) {
+      if (h->dbg.n < 32 * 16) CK(h->dbg.alloc(32 * 16));
+      CK(cudaMemsetAsync(h->dbg.p, 0, sizeof(long long) * 32 * 16, h->stream));
+      t.dbg = h->dbg.p;
+    }
     if (want_obj) {
       CK(cudaFuncSetAttribute(k_assign_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
       k_assign_tc3<true><<<grid_tc, A3_THREADS, smem_tc, h->stream>>>(t);
@@ -512,6 +524,19 @@ int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_o
       k_assign_tc3<false><<<grid_tc, A3_THREADS, smem_tc, h->stream>>>(t);
     }
     CKL();
+    if (tracing) {
+      std::vector<long long> st(32 * 16);
+      CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (FILE* f = fopen("gpurun_out/assign_trace.txt", "w")) {
+        for (int i = 0; i < 32; ++i) {
+          fprintf(f, "%d", i);
+          for (int k = 0; k < 16; ++k) fprintf(f, " %lld", st[(size_t)i * 16 + k] ? st[(size_t)i * 16 + k] - st[0] : -1);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
     h->R_user_set = false;
     if (plan_mode) {
       // O, E of the assignment = the sums of the blocks' removal terms (harmony.cpp:226-227)
@@ -623,58 +648,61 @@ int check_convergence_host(hb_handle* h, int type, int* out) {
 // ---- update-order plan (buffers hold plan_rounds rounds, two sets) ----------------------------------
 // Phase A: the block of every local cell in round t (harmony.cpp:272-291: position in the shuffled order / cells
 // per block).  Phase B: the round's rows sorted by (block, tuple, block in the next round) + the derived tables.
-int plan_blocks(hb_handle* h, int t, const int64_t* perm_d /* device, N_global, or null */, int set, cudaStream_t st) {
+// rounds [t, t + nt) of a buffer set in one launch (blockIdx.y = round)
+int plan_blocks(hb_handle* h, int t, int nt, const int64_t* perm_d /* device, nt x N_global, or null */, int set, cudaStream_t st) {
   RegionScope rs(h, "plan");
   const int64_t n = h->n;
   const size_t R0 = (size_t)set * h->plan_rounds;  // first round slot of this buffer set
   int* blk_of = h->blk_of.p + (R0 + t) * n;
   if (perm_d) {
-    CK(cudaMemsetAsync(blk_of, 0xff, sizeof(int) * (size_t)n, st));
-    k_plan_block_injected<<<grid_for(h->N_global, 256, h->num_sms * 8), 256, 0, st>>>(
+    CK(cudaMemsetAsync(blk_of, 0xff, sizeof(int) * (size_t)n * nt, st));
+    k_plan_block_injected<<<dim3(grid_for(h->N_global, 256, h->num_sms * 8), nt), 256, 0, st>>>(
         perm_d, h->N_global, h->cell_offset, n, h->inv_sort.p, h->cpb, h->nb, blk_of, h->err_flag.p);
     CKL();
   } else {
-    uint64_t key = hb_mix64(h->seed ^ hb_mix64(h->round_counter + 0x1234567ull));
-    k_plan_block_native<<<grid_for(n, 256, h->num_sms * 8), 256, 0, st>>>(
-        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, h->nb, h->half_bits, key, blk_of);
+    k_plan_block_native<<<dim3(grid_for(n, 256, h->num_sms * 8), nt), 256, 0, st>>>(
+        h->N_global, h->cell_offset, n, h->sort_perm.p, h->cpb, h->nb, h->half_bits, h->seed, h->round_counter, blk_of);
     CKL();
   }
-  h->round_counter++;
+  h->round_counter += (uint64_t)nt;
   return 0;
 }
-int plan_sort(hb_handle* h, int t, bool has_next, int set, cudaStream_t st, bool tiles = false) {
+// counting sort of rounds [t, t + nt) (nt <= plan_batch: the histogram scratch holds that many rounds); round
+// t + nt - 1 has a next round iff last_has_next
+int plan_sort(hb_handle* h, int t, int nt, bool last_has_next, int set, cudaStream_t st, bool tiles = false) {
   RegionScope rs(h, "plan");
   const int nb = h->nb, J = h->J, nc = h->nchunks, nsub = h->plan_nsub;
   const int64_t n = h->n;
   const int S = nb * J;
   const size_t R0 = (size_t)set * h->plan_rounds;
   const int* blk_of = h->blk_of.p + (R0 + t) * n;
-  const int* blk_next = has_next ? h->blk_of.p + (R0 + t + 1) * n : nullptr;
   int* order = h->order.p + (R0 + t) * n;
   int* seg_start = h->seg_start.p + (R0 + t) * (S + 1);
   int* tile_base = h->tile_base.p + (R0 + t) * (S + 1);
   const size_t per_warp = sizeof(int) * (size_t)nb * nsub;
   const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));  // warps per block
   const size_t sm = per_warp * wpb;
-  k_plan_hist<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(blk_of, blk_next, h->chunk_start.p, h->chunk_q0.p, h->chunk_nq.p, nc,
-                                                          nb, nsub, h->H.p, h->err_flag.p);
+  const int with_next = last_has_next ? nt : nt - 1;
+  k_plan_hist<<<dim3((nc + wpb - 1) / wpb, nt), wpb * 32, sm, st>>>(blk_of, nullptr, h->chunk_start.p, h->chunk_q0.p,
+                                                                   h->chunk_nq.p, nc, nb, nsub, h->H.p, h->err_flag.p, n,
+                                                                   with_next);
   CKL();
-  k_scan_exclusive<<<1, 1024, 0, st>>>(h->H.p, (int64_t)nb * nsub * nc, nullptr);
+  k_scan_exclusive<<<nt, 1024, 0, st>>>(h->H.p, (int64_t)nb * nsub * nc, nullptr);
   CKL();
-  k_plan_scatter<<<(nc + wpb - 1) / wpb, wpb * 32, sm, st>>>(
-      blk_of, blk_next, h->chunk_start.p, h->chunk_q0.p, h->chunk_nq.p, nc, nb, nsub, h->H.p, order,
-      (t > 0) ? h->blk_of.p + (R0 + t - 1) * n : nullptr, (h->use_v2 && !h->use_v4) ? h->prev_at.p + (R0 + t) * n : nullptr,
-      h->use_v4 ? h->next_at.p + (R0 + t) * n : nullptr);
+  k_plan_scatter<<<dim3((nc + wpb - 1) / wpb, nt), wpb * 32, sm, st>>>(
+      blk_of, nullptr, h->chunk_start.p, h->chunk_q0.p, h->chunk_nq.p, nc, nb, nsub, h->H.p, order, nullptr,
+      (h->use_v2 && !h->use_v4) ? h->prev_at.p + (R0 + t) * n : nullptr, h->use_v4 ? h->next_at.p + (R0 + t) * n : nullptr, n,
+      with_next, t > 0 ? 1 : 0);
   CKL();
-  k_plan_segments<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(h->H.p, h->tuple_chunk0.p, nc, nb, nsub, J, (int)n, seg_start,
-                                                           tile_base);
+  k_plan_segments<<<dim3(grid_for(S + 1, 256, 64), nt), 256, 0, st>>>(h->H.p, h->tuple_chunk0.p, nc, nb, nsub, J, (int)n,
+                                                                       seg_start, tile_base);
   CKL();
   if (h->use_v2 && h->aligned_ranges) {
-    k_plan_ranges<<<(nb * h->coop_grid + 127) / 128, 128, 0, st>>>(seg_start, nb, J, h->coop_grid,
-                                                        h->ranges.p + (R0 + t) * nb * h->coop_grid);
+    k_plan_ranges<<<dim3((nb * h->coop_grid + 127) / 128, nt), 128, 0, st>>>(seg_start, nb, J, h->coop_grid,
+                                                                            h->ranges.p + (R0 + t) * nb * h->coop_grid);
     CKL();
   }
-  if (tiles) {  // tile offsets of the first-generation update kernels
+  if (tiles) {  // tile offsets of the first-generation update kernels (single round)
     k_plan_tilecount<<<grid_for(S + 1, 256, 64), 256, 0, st>>>(seg_start, S, tile_base);
     CKL();
     k_scan_exclusive<<<1, 1024, 0, st>>>(tile_base, (int64_t)S + 1, nullptr);
@@ -684,8 +712,11 @@ int plan_sort(hb_handle* h, int t, bool has_next, int set, cudaStream_t st, bool
 }
 // all T rounds of a cluster_cpp call (orders: device, T x N_global, or null for the native keyed orders)
 int build_plans(hb_handle* h, int T, const int64_t* orders_d, int set, cudaStream_t st) {
-  for (int t = 0; t < T; ++t) TRY(plan_blocks(h, t, orders_d ? orders_d + (size_t)t * (size_t)h->N_global : nullptr, set, st));
-  for (int t = 0; t < T; ++t) TRY(plan_sort(h, t, t + 1 < T, set, st));
+  if (T > 0) TRY(plan_blocks(h, 0, T, orders_d, set, st));
+  for (int t = 0; t < T; t += h->plan_batch) {
+    const int nt = std::min(h->plan_batch, T - t);
+    TRY(plan_sort(h, t, nt, t + nt < T, set, st));
+  }
   if (T > 0 && h->use_tc_assign && h->use_v4) {
     // 128-row tiles of round 0, one (block, tuple) segment at a time: the assignment step of the call runs in this order
     RegionScope rs(h, "plan");
@@ -705,8 +736,8 @@ int build_plans(hb_handle* h, int T, const int64_t* orders_d, int set, cudaStrea
 }
 // one round into slot 0 of set 0 (per-round paths: first-generation kernels, legacy centroid step)
 int build_plan_single(hb_handle* h, const int64_t* perm_d, cudaStream_t st) {
-  TRY(plan_blocks(h, 0, perm_d, 0, st));
-  return plan_sort(h, 0, false, 0, st, true);
+  TRY(plan_blocks(h, 0, 1, perm_d, 0, st));
+  return plan_sort(h, 0, 1, false, 0, st, true);
 }
 
 // ---- v1: one update_R sweep (harmony.cpp:269-342), three launches per block step ------------------
@@ -977,6 +1008,7 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.sigma_uniform = h->sigma_uniform ? 1 : 0;
   a.sigma0 = h->sigma0;
   a.nbatch = h->u4_nbatch;
+  a.ring_rows = h->u5_ring_rows;
   a.coop = 1;
   a.dbg = (h->dbg_cta >= 0) ? h->dbg.p : nullptr;
   a.dbg_cta = h->dbg_cta;
@@ -1033,8 +1065,32 @@ int upd4_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
   CKL();
   return 0;
 }
+template <int NV, bool SIGU>
+int upd5_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
+  const size_t smem = upd5_smem_bytes(NV, a.ring_rows, a.KS);
+  CK(cudaFuncSetAttribute(k_update_steps5<NV, SIGU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.coop = cooperative ? 1 : 0;
+  Upd4Launch lp;
+  lp.a = a;
+  if (h->use_xch) lp.x = h->xch;
+  if (cooperative) {
+    void* args[] = {&lp};
+    CK(cudaLaunchCooperativeKernel((void*)k_update_steps5<NV, SIGU>, dim3(h->coop_grid), dim3(U5_THREADS), args, smem,
+                                   h->stream));
+  } else {
+    k_update_steps5<NV, SIGU><<<h->coop_grid, U5_THREADS, smem, h->stream>>>(lp);
+  }
+  CKL();
+  return 0;
+}
 int upd4_launch(hb_handle* h, Upd4Args a, bool cooperative) {
   const bool su = h->sigma_uniform;  // the default: scalar sigma (objective terms simplify)
+  if (h->use_v5) {
+    switch (upd4_nv(h->KS)) {
+      case 1: return su ? upd5_launch_nv<1, true>(h, a, cooperative) : upd5_launch_nv<1, false>(h, a, cooperative);
+      case 2: return su ? upd5_launch_nv<2, true>(h, a, cooperative) : upd5_launch_nv<2, false>(h, a, cooperative);
+    }
+  }
   switch (upd4_nv(h->KS)) {
     case 1: return su ? upd4_launch_nv<1, true>(h, a, cooperative) : upd4_launch_nv<1, false>(h, a, cooperative);
     case 2: return su ? upd4_launch_nv<2, true>(h, a, cooperative) : upd4_launch_nv<2, false>(h, a, cooperative);
@@ -1795,6 +1851,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   h->aligned_ranges = (2 * J <= h->coop_grid);
   h->u4_nbatch = upd4_nbatch(KS, smem_limit);
   h->use_v4 = !force_v1 && !force_v2 && h->aligned_ranges && h->u4_nbatch > 0;
+  h->u5_ring_rows = upd5_ring_rows(KS, smem_limit);
+  h->use_v5 = h->use_v4 && h->u5_ring_rows > 0 && (uint64_t)N * (uint64_t)KS < (1ull << 32) && getenv("HB_UPDATE_V4") == nullptr;
   h->use_v2 = h->use_v4 || (!force_v1 && (KS <= 256) && (J <= 8192) && upd_smem_bytes(h) <= smem_limit);
   h->plan_nsub = (h->use_v4 && h->nb <= 64) ? h->nb : 1;
   h->plan_rounds = Tplan;
@@ -1857,7 +1915,11 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->next_at.alloc(2 * (size_t)Tplan * N));
   else
     CK(h->prev_at.alloc(2 * (size_t)Tplan * N));
-  CK(h->H.alloc((size_t)h->nb * h->plan_nsub * h->nchunks));
+  {  // histogram scratch of the plan's counting sort: as many rounds per launch as fit 64 MB (at most 8)
+    const size_t per_round = (size_t)h->nb * h->plan_nsub * h->nchunks;
+    h->plan_batch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)Tplan, ((size_t)16 << 20) / std::max<size_t>(1, per_round)}));
+    CK(h->H.alloc(per_round * h->plan_batch));
+  }
   CK(h->chunk_q0.alloc(h->nchunks));
   CK(h->chunk_nq.alloc(h->nchunks));
   CK(h->seg_start.alloc(2 * (size_t)Tplan * ((size_t)h->nb * J + 1)));

@@ -374,6 +374,8 @@ __global__ void k_assign_finalize_plan(const float* __restrict__ acc, int nb, co
 __global__ void k_plan_block_injected(const int64_t* __restrict__ update_order, int64_t N_global, int64_t cell_offset,
                                       int64_t n_local, const int* __restrict__ inv_sort, uint32_t cpb, int nb,
                                       int* __restrict__ blk_of, int* __restrict__ err_flag) {
+  update_order += (size_t)blockIdx.y * (size_t)N_global;  // blockIdx.y: round of the call
+  blk_of += (size_t)blockIdx.y * (size_t)n_local;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N_global;
        p += (int64_t)gridDim.x * blockDim.x) {
     int64_t g = update_order[p];
@@ -388,10 +390,16 @@ __global__ void k_plan_block_injected(const int64_t* __restrict__ update_order, 
     blk_of[inv_sort[l]] = (int)b;
   }
 }
-// Native order: position of global cell g is hb_permute(g) (a keyed bijection of [0, N)).
+// Native order: position of global cell g is hb_permute(g) (a keyed bijection of [0, N)); the key of a round
+// depends on (seed, round counter) only.  blockIdx.y: round of the call.
+__host__ __device__ __forceinline__ uint64_t plan_round_key(uint64_t seed, uint64_t round_counter) {
+  return hb_mix64(seed ^ hb_mix64(round_counter + 0x1234567ull));
+}
 __global__ void k_plan_block_native(int64_t N_global, int64_t cell_offset, int64_t n_local,
                                     const int* __restrict__ sort_perm, uint32_t cpb, int nb, int half_bits,
-                                    uint64_t key, int* __restrict__ blk_of) {
+                                    uint64_t seed, uint64_t round_counter0, int* __restrict__ blk_of) {
+  const uint64_t key = plan_round_key(seed, round_counter0 + blockIdx.y);
+  blk_of += (size_t)blockIdx.y * (size_t)n_local;
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n_local;
        s += (int64_t)gridDim.x * blockDim.x) {
     uint64_t g = (uint64_t)(cell_offset + sort_perm[s]);
@@ -414,12 +422,17 @@ __device__ __forceinline__ size_t plan_hidx(int blk, int sub, int c, int nchunks
 // One warp per chunk: H[..] = #cells of the chunk with (block, next-round block) = (blk, sub).
 __global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restrict__ blk_next,
                             const int* __restrict__ chunk_start, const int* __restrict__ cq0, const int* __restrict__ cnq,
-                            int nchunks, int nb, int nsub, int* __restrict__ H, int* __restrict__ err_flag) {
+                            int nchunks, int nb, int nsub, int* __restrict__ H, int* __restrict__ err_flag, int64_t n_local,
+                            int rounds_with_next) {
   extern __shared__ int sh[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cnt = sh + warp * nb * nsub;
   int c = blockIdx.x * (blockDim.x >> 5) + warp;
   if (c >= nchunks) return;
+  // blockIdx.y: round of the batch (rounds are n_local apart in blk_of; blk_next of round y is blk_of of round y + 1)
+  blk_of += (size_t)blockIdx.y * (size_t)n_local;
+  blk_next = ((int)blockIdx.y < rounds_with_next) ? blk_of + n_local : nullptr;
+  H += (size_t)blockIdx.y * (size_t)nb * nsub * nchunks;
   for (int j = lane; j < nb * nsub; j += 32) cnt[j] = 0;
   __syncwarp();
   int s0 = chunk_start[c], s1 = chunk_start[c + 1];
@@ -438,6 +451,8 @@ __global__ void k_plan_hist(const int* __restrict__ blk_of, const int* __restric
 // Single-CTA exclusive scan of an int array (in place), total written to *total.  Every warp owns a contiguous
 // range and walks it 32 consecutive elements at a time (coalesced): pass 1 sums, pass 2 scans with a carry.
 __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data, int64_t n, int* __restrict__ total) {
+  data += (size_t)blockIdx.x * (size_t)n;  // blockIdx.x: independent arrays of n elements, back to back
+  if (total) total += blockIdx.x;
   __shared__ int wsum[32];
   __shared__ int carry_all;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -481,12 +496,23 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data,
 __global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __restrict__ blk_next,
                                const int* __restrict__ chunk_start, const int* __restrict__ cq0, const int* __restrict__ cnq,
                                int nchunks, int nb, int nsub, const int* __restrict__ Hoff, int* __restrict__ order,
-                               const int* __restrict__ blk_prev, int* __restrict__ prev_at, int* __restrict__ next_at) {
+                               const int* __restrict__ blk_prev, int* __restrict__ prev_at, int* __restrict__ next_at,
+                               int64_t n_local, int rounds_with_next, int first_has_prev) {
   extern __shared__ int sh[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cur = sh + warp * nb * nsub;
   int c = blockIdx.x * (blockDim.x >> 5) + warp;
   if (c >= nchunks) return;
+  {  // blockIdx.y: round of the batch
+    const size_t ro = (size_t)blockIdx.y * (size_t)n_local;
+    blk_of += ro;
+    blk_next = ((int)blockIdx.y < rounds_with_next) ? blk_of + n_local : nullptr;
+    blk_prev = (blockIdx.y > 0 || first_has_prev) ? blk_of - n_local : nullptr;
+    Hoff += (size_t)blockIdx.y * (size_t)nb * nsub * nchunks;
+    order += ro;
+    if (prev_at) prev_at += ro;
+    if (next_at) next_at += ro;
+  }
   for (int j = lane; j < nb * nsub; j += 32) cur[j] = Hoff[plan_hidx(j / nsub, j % nsub, c, nchunks, nsub, cq0, cnq)];
   __syncwarp();
   int s0 = chunk_start[c], s1 = chunk_start[c + 1];
@@ -520,6 +546,8 @@ __global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restr
                                 int nb, int nsub, int J, int n_local, int* __restrict__ seg_start,
                                 int* __restrict__ tile_base) {
   int S = nb * J;
+  Hoff += (size_t)blockIdx.y * (size_t)nb * nsub * nchunks;  // blockIdx.y: round of the batch
+  seg_start += (size_t)blockIdx.y * (S + 1);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s <= S; s += gridDim.x * blockDim.x) {
     int v;
     if (s == S) {
@@ -538,6 +566,8 @@ __global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restr
 __global__ void k_plan_ranges(const int* __restrict__ seg_start, int nb, int J, int G, int4* __restrict__ ranges) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nb * G) return;
+  seg_start += (size_t)blockIdx.y * ((size_t)nb * J + 1);  // blockIdx.y: round of the batch
+  ranges += (size_t)blockIdx.y * (size_t)nb * G;
   const int j = idx / G, me_cta = idx - j * G;
   const int* segs = seg_start + (size_t)j * J;
   const int b0 = segs[0];
