@@ -1009,6 +1009,10 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.sigma0 = h->sigma0;
   a.nbatch = h->u4_nbatch;
   a.ring_rows = h->u5_ring_rows;
+  {
+    static const int flags = getenv("HB_U5_FLAGS") ? atoi(getenv("HB_U5_FLAGS")) : 0;
+    a.dbg_flags = flags;
+  }
   a.coop = 1;
   a.dbg = (h->dbg_cta >= 0) ? h->dbg.p : nullptr;
   a.dbg_cta = h->dbg_cta;

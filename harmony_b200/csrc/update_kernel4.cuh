@@ -71,6 +71,7 @@ struct Upd4Args {
   float sigma0;
   int nbatch;            // ring slots (batches of U4_BR rows)
   int ring_rows;         // update_kernel5.cuh: rows of every warp's private ring
+  int dbg_flags;         // timing experiments only (HB_U5_FLAGS): 1 = no remT reductions, 2 = no R stores (results invalid)
   int coop;              // 1: one launch covers many steps (counters + in-kernel fold); 0: single-step launch
   long long* dbg;        // optional [steps][8] globaltimer stamps of CTA dbg_cta (null = off)
   int dbg_cta;

@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
     const int q = rg.z;
     const int my_rows = chunk_rows(rg);
     const int t = s / nb, j = s - t * nb;
-    const bool writeR = t >= a.write_from;
-    const bool has_next = t < a.has_next_from;
+    const bool writeR = t >= a.write_from && !(a.dbg_flags & 2);
+    const bool has_next = t < a.has_next_from && !(a.dbg_flags & 1);
     if (a.coop) {
       if (s > a.s_begin) wait_for(cntU + s - 1);  // add_{s-1}, ring(s-1); at j == 0 also: round t-1 is complete
       if (multi && s >= 1) wait_slot(s + 1);      // ... on every rank: add_{s-1} lives in slot(s) = index s + 1
