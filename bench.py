@@ -30,35 +30,66 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CELLS_PER_GPU = 1_000_000
-D, K, B_LEVELS, T = 50, 100, 20, 4
+T = 4
 N_TYPES = 30
-METRIC = "cells/sec/Harmony-iteration (50 PCs, K=100)"
-# algorithmic bytes per cell per Harmony iteration, fp32 state, T = 4
-ALGO_BYTES_PER_CELL_ITER = 4 * (K * (3 + 2 * T) + D * (5 + T)) + 4 * (T + 2)   # 6224 for K=100, d=50
+# BASELINE.json configs 3 / 4 / 5 as PER-GPU shards (config 4: 10M cells over 8 GPUs, config 5: 50M over 8);
+# the headline metric is quoted on config 3.  Level counts beyond config 3's are SURVEY.md 8(d)'s stated choice.
+WORKLOADS = {
+    "c3": dict(cells_per_gpu=1_000_000, d=50, K=100, B_vec=[20],
+               name="BASELINE.json config 3 per GPU", metric="cells/sec/Harmony-iteration (50 PCs, K=100)"),
+    "c4": dict(cells_per_gpu=1_250_000, d=50, K=100, B_vec=[10, 40],
+               name="BASELINE.json config 4 (10M cells, dataset + donor) as the per-GPU shard of 8",
+               metric="cells/sec/Harmony-iteration (50 PCs, K=100, 2 covariates)"),
+    "c5": dict(cells_per_gpu=6_250_000, d=100, K=200, B_vec=[10, 40, 6],
+               name="BASELINE.json config 5 (50M cells, 3 covariates) as the per-GPU shard of 8",
+               metric="cells/sec/Harmony-iteration (100 PCs, K=200, 3 covariates)"),
+}
+W = dict(WORKLOADS["c3"])   # the active workload (set in main)
+
+
+def algo_bytes_per_cell_iter(K, d):
+    """algorithmic bytes per cell per Harmony iteration, fp32 state, T rounds."""
+    return 4 * (K * (3 + 2 * T) + d * (5 + T)) + 4 * (T + 2)   # 6224 for K=100, d=50; 12424 for K=200, d=100
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def synth_shard(n, cell_offset, seed, d=D, n_levels=B_LEVELS, n_types=N_TYPES):
-    """SURVEY.md §8(d) generator: Z[i,j] = sd_j (M[t_i,j] + 0.5 S[b_i,j] + 0.6 eps), sd_j = 10/sqrt(1+j);
-    type probabilities ~ Dirichlet(2), batch probabilities ~ LogNormal(0, 0.5).  Global parameters come
-    from `seed`, the per-cell draws from (seed, cell_offset) so shards are consistent for any world size."""
+def synth_shard(n, cell_offset, seed, d=None, B_vec=None, n_types=N_TYPES):
+    """SURVEY.md 8(d) generator: Z[i,j] = sd_j (M[t_i,j] + sum_c 0.5 S_c[b_ci,j] + 0.6 eps), sd_j = 10/sqrt(1+j);
+    type probabilities ~ Dirichlet(2), level probabilities ~ LogNormal(0, 0.5).  Further covariates are NESTED:
+    every level of covariate c >= 1 ("donor") belongs to one level of covariate 0 ("dataset", levels dealt round
+    robin), a third covariate is a fixed property of the donor -> J = #donors joint tuples.  Global parameters
+    come from `seed`, the per-cell draws from (seed, cell_offset) so shards are consistent for any world size.
+    Returns Z (float64, n x d) and the level ids (int32, n x C, per-covariate numbering)."""
+    d = W["d"] if d is None else d
+    B_vec = W["B_vec"] if B_vec is None else B_vec
     g = np.random.default_rng(seed)
     M = g.standard_normal((n_types, d)).astype(np.float32)
-    S = g.standard_normal((n_levels, d)).astype(np.float32)
+    S = [g.standard_normal((b, d)).astype(np.float32) for b in B_vec]
     p_type = g.dirichlet(np.full(n_types, 2.0))
-    p_lvl = g.lognormal(0.0, 0.5, n_levels)
-    p_lvl /= p_lvl.sum()
+    p_lvl = [g.lognormal(0.0, 0.5, b) for b in B_vec]
+    chem_of_donor = g.integers(0, B_vec[2], B_vec[1]) if len(B_vec) > 2 else None
     sd = (10.0 / np.sqrt(1.0 + np.arange(d))).astype(np.float32)
     r = np.random.default_rng([seed, cell_offset])
     t = r.choice(n_types, n, p=p_type)
-    b = r.choice(n_levels, n, p=p_lvl).astype(np.int32)
-    Z = M[t] + 0.5 * S[b] + 0.6 * r.standard_normal((n, d), dtype=np.float32)
+    lv = np.empty((n, len(B_vec)), dtype=np.int32)
+    lv[:, 0] = r.choice(B_vec[0], n, p=p_lvl[0] / p_lvl[0].sum())
+    if len(B_vec) > 1:
+        parent = np.arange(B_vec[1]) % B_vec[0]
+        for p in range(B_vec[0]):
+            cand = np.flatnonzero(parent == p)
+            sel = np.flatnonzero(lv[:, 0] == p)
+            w = p_lvl[1][cand]
+            lv[sel, 1] = r.choice(cand, sel.size, p=w / w.sum())
+    if len(B_vec) > 2:
+        lv[:, 2] = chem_of_donor[lv[:, 1]]
+    Z = M[t] + 0.6 * r.standard_normal((n, d), dtype=np.float32)
+    for c in range(len(B_vec)):
+        Z += 0.5 * S[c][lv[:, c]]
     Z *= sd[None, :]
-    return Z.astype(np.float64), b
+    return Z.astype(np.float64), lv
 
 
 def host_Y0(Z, k, seed):
@@ -76,11 +107,14 @@ def host_Y0(Z, k, seed):
     return Y
 
 
-def setup_kwargs(b, n_levels=B_LEVELS):
-    theta = np.full(n_levels, 2.0)
-    return dict(phi=b.reshape(-1, 1), sigma=np.full(K, 0.1), theta=theta, lambda_=None, alpha=0.2,
-                max_iter_kmeans=T, epsilon_kmeans=1e-3, epsilon_harmony=-np.inf, K=K, block_size=0.05,
-                B_vec=np.array([n_levels], dtype=np.int32), cutoff=1e-5)
+def setup_kwargs(lv):
+    """Defaults of R/ui.R:95-100 / R/harmony_option.R:33-40; level ids renumbered globally (covariate c's levels
+    follow those of covariate c - 1), as R/ui.R:219-231 builds Phi."""
+    B_vec = np.asarray(W["B_vec"], dtype=np.int32)
+    off = np.concatenate([[0], np.cumsum(B_vec)[:-1]]).astype(np.int32)
+    return dict(phi=np.ascontiguousarray(lv + off[None, :]), sigma=np.full(W["K"], 0.1), theta=np.full(int(B_vec.sum()), 2.0),
+                lambda_=None, alpha=0.2, max_iter_kmeans=T, epsilon_kmeans=1e-3, epsilon_harmony=-np.inf, K=W["K"],
+                block_size=0.05, B_vec=B_vec, cutoff=1e-5)
 
 
 class ClockSampler(threading.Thread):
@@ -161,12 +195,29 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def measured_traffic(kernel, config, n_local):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    ncu --set full capture of this workload (profiles/traffic.json: {config: {kernel: {"cells": n, "bytes": b}}});
+    None when no capture of this kernel at this shard size has been committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[config][kernel]
+        return float(t["bytes"]) if int(t["cells"]) == int(n_local) else None
+    except Exception:
+        return None
+
+
+def cpu_sample_cells():
+    """Bounded CPU sample: ~200k cells at K=100, d=50 (about 5 s per oracle iteration), fewer for wider shapes."""
+    return int(max(20_000, min(200_000, 200_000 * (100 * 50) / (W["K"] * W["d"]))))
+
+
 def cpu_reference_run(n_cells, iters, threads, seed=20260925):
     """Times the CPU oracle (restatement of the reference's Armadillo/OpenBLAS path) on host cores."""
     from oracle.oracle import OracleHarmony, load_blas
     blas = load_blas(threads)
     Z, b = synth_shard(n_cells, 0, seed)
     kw = setup_kwargs(b)
+    K = W["K"]
     Y0 = host_Y0(Z, K, 1)
     o = OracleHarmony()
     o.setup(Z, kw["phi"], kw["B_vec"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, 1e-5)
@@ -190,7 +241,7 @@ def run_reference(args):
     if rank != 0:
         return
     ncpu = os.cpu_count() or 1
-    n_sample = int(args.ref_cells)
+    n_sample = int(args.ref_cells) if args.ref_cells > 0 else cpu_sample_cells()
     steps = max(1, min(args.steps, 3))
     # the reference only threads its BLAS call (R/ui.R:123-128); time it with all host threads and with the
     # reference default ncores = 1 and report the faster of the two (skinny sgemm often loses with threads)
@@ -198,11 +249,12 @@ def run_reference(args):
     t_one, _ = cpu_reference_run(n_sample, steps, 1) if ncpu > 1 else (t_all, blas)
     t_iter, cores = (t_all, ncpu) if t_all <= t_one else (t_one, 1)
     v = n_sample / t_iter
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s/iter", "n_gpus": args.gpus,
+    D, K = W["d"], W["K"]
+    line = {"impl": "reference", "metric": W["metric"], "value": v, "unit": "cells/s/iter", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": t_iter * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic {n_sample} cells x {D} PCs, 1 covariate ({B_LEVELS} batches), K={K}"
-                                   " (bounded sample of config 3; the algorithm is O(N))"},
+            "config": {"workload": f"synthetic {n_sample} cells x {D} PCs, {len(W['B_vec'])} covariate(s) (levels {W['B_vec']}), "
+                                   f"K={K} (bounded sample of {W['name']}; the algorithm is O(N))"},
             "cpu_baseline": {"value": v, "unit": "cells/s/iter", "cores": cores, "kind": "port",
                              "sample": f"{n_sample} cells, {steps} timed iteration(s), BLAS={os.path.basename(blas)}; "
                                        f"all {ncpu} threads: {n_sample / t_all:.0f} cells/s/iter, 1 thread: "
@@ -217,11 +269,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells-per-gpu", type=int, default=CELLS_PER_GPU)
+    ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS), help="BASELINE.json workload (per-GPU shard)")
+    ap.add_argument("--cells-per-gpu", type=int, default=0, help="override the workload's shard size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-cells", type=int, default=200_000, help="cells of the bounded CPU sample (--impl reference)")
+    ap.add_argument("--ref-cells", type=int, default=0, help="cells of the bounded CPU sample (--impl reference); 0 = by workload")
     args = ap.parse_args()
+    W.clear()
+    W.update(WORKLOADS[args.config])
+    if args.cells_per_gpu <= 0:
+        args.cells_per_gpu = W["cells_per_gpu"]
+    D, K, METRIC = W["d"], W["K"], W["metric"]
+    ALGO_BYTES_PER_CELL_ITER = algo_bytes_per_cell_iter(K, D)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -261,7 +320,7 @@ def main():
         dist.broadcast(t, 0)
         return (rank, world, bytes(t.cpu().tolist()), N_global, rank * n_local)
 
-    seed = 20260922 + 3
+    seed = 20260922 + int(args.config[1:])
     Z, b = synth_shard(n_local, rank * n_local, seed)
     kw = setup_kwargs(b)
     Y0 = host_Y0(Z, K, 1) if rank == 0 else np.zeros((K, D))
@@ -359,7 +418,7 @@ def main():
         top = max(kernels, key=lambda r: kernels[r]["share_of_step"])
         # DRAM bytes of one launch of the dominant kernel from the ncu --set full capture of this exact
         # workload (profiles/r01_final_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum); null otherwise
-        traffic = 3.357287e9 + 0.395527e9 if (top == "k_update_steps" and n_local == CELLS_PER_GPU) else None
+        traffic = measured_traffic(top, args.config, n_local)
         roofline = dict(kernel=top, traffic=traffic, peak_kind=peak_kind, **kernels[top])
     step_ach = ALGO_BYTES_PER_CELL_ITER * n_local / (ms_per_step * 1e-3) / 1e9
 
@@ -398,21 +457,22 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_sample = 200_000
+        n_sample = cpu_sample_cells()
         t_iter, blas = cpu_reference_run(n_sample, 2, 1)
         cpu = {"value": n_sample / t_iter, "unit": "cells/s/iter", "cores": 1, "kind": "port",
-               "sample": f"{n_sample} cells x {D} PCs, K={K}, {B_LEVELS} batches, 2 timed iterations, single thread "
+               "sample": f"{n_sample} cells x {D} PCs, K={K}, levels {W['B_vec']}, 2 timed iterations, single thread "
                          f"(reference default ncores=1), sgemm from {os.path.basename(blas)}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "cells/s/iter", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"synthetic {N_global} cells x {D} PCs, 1 covariate ({B_LEVELS} batches), "
-                                       f"K={K}, T={T}, block_size=0.05 (BASELINE.json config 3 per GPU)",
+                "config": {"workload": f"synthetic {N_global} cells x {D} PCs, {len(W['B_vec'])} covariate(s) (levels "
+                                       f"{W['B_vec']}), K={K}, T={T}, block_size=0.05 ({W['name']})",
+                           "config_id": args.config,
                            "cells_per_gpu": n_local, "parallelism": f"cells sharded x{world}",
                            "switches": sorted(k for k in os.environ if k.startswith("HB_")),  # experimental paths, if any
-                           "l2": "state (U,R,Z = 1.2 GB per GPU) is ~10x larger than the 126 MB L2"},
+                           "l2": f"state (U,R,Z = {n_local * (2 * KS + 2 * DS) * 4 / 1e9:.1f} GB per GPU) is far larger than the 126 MB L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline,
                 "roofline_kernels": {r: {k2: (round(v2, 4) if isinstance(v2, float) else v2) for k2, v2 in kv.items()}

@@ -93,6 +93,9 @@ def lib():
     L.hb_debug_permute.restype = ctypes.c_uint64
     L.hb_debug_permute.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, I]
     L.hb_debug_update_geometry.argtypes = [I, I, ctypes.POINTER(I64)]
+    L.hb_debug_kmeans_uniform.restype = D
+    L.hb_debug_kmeans_uniform.argtypes = [P, ctypes.c_uint64, ctypes.c_uint64]
+    L.hb_debug_kmeans_cells.argtypes = [P, P]
     L.hb_debug_widen.argtypes = [P, P, I64, I]
     _LIB = L
     return L

@@ -293,9 +293,21 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
     const int bcol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     float okd = 0.f, oent = 0.f;
     int it = 0;
+    // tile records one tile ahead: the loads overlap the previous tile's epilogue instead of opening every tile
+    int len_n = 0, tq_n = 0, blk_n = 0;
+    if (my_first < a.ntiles) {
+      len_n = __ldg(a.tile_len + my_first);
+      tq_n = __ldg(a.tile_tuple + my_first);
+      blk_n = a.tile_blk ? __ldg(a.tile_blk + my_first) : 0;
+    }
     for (int tile = my_first; tile < a.ntiles; tile += stride, ++it) {
       const int acc = it & 1;
-      const int len = __ldg(a.tile_len + tile), tq = __ldg(a.tile_tuple + tile);
+      const int len = len_n, tq = tq_n, tblk = blk_n;
+      if (tile + stride < a.ntiles) {
+        len_n = __ldg(a.tile_len + tile + stride);
+        tq_n = __ldg(a.tile_tuple + tile + stride);
+        blk_n = a.tile_blk ? __ldg(a.tile_blk + tile + stride) : 0;
+      }
       const bool live = r < len;
       umma::mbar_wait(t_full + acc, (it >> 1) & 1);
       umma::fence_after_sync();
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
       const float rn = rnorm[(size_t)(it % A3_RING_N) * TC_TM + r];
       const uint32_t trow = tmem + acc * 128 + ((uint32_t)(q * 32) << 16);
       float ev[64];                        // exp(u) of this thread's columns
-      float ssum = 0.f, A1 = 0.f, B1 = 0.f, S1 = 0.f;  // sum e, sum e*dist, sum sigma*e*u, sum sigma*e
+      float ssum = 0.f, A1 = 0.f, S1 = 0.f;  // sum e, sum e*dist, sum sigma*e*u, sum sigma*e
       float* urow = Ust + (size_t)r * SS;
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
@@ -462,7 +474,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) k_assign_tc3(Assign3Args a) {
         float* drs;
         if (a.tile_blk) {
           const size_t XH = (size_t)a.B * KS + KS;
-          float* slot = a.acc + (size_t)(__ldg(a.tile_blk + tile) + 1) * 2 * XH;
+          float* slot = a.acc + (size_t)(tblk + 1) * 2 * XH;
           dO = slot + XH;              // rem_O
           drs = dO + (size_t)a.B * KS;  // rem_rs
         } else {

@@ -291,9 +291,7 @@ struct hb_handle {
   DevBuf<float> Rkeep, OEkeep;   // R / O,E saved around the distance-only assignment of that step
   DevBuf<double> objkeep;
   bool use_v4 = false;   // single-pass persistent update kernel (update_kernel4.cuh): the default
-  int u4_nbatch = 0;     // its ring size (batches of U4_BR rows)
   int u5_ring_rows = 0;  // rows of a warp's private ring (update_kernel5.cuh); 0: that kernel cannot run this row width
-  bool use_v5 = false;
   int plan_batch = 1;    // rounds sorted per launch (size of the histogram scratch)
   int plan_nsub = 1;     // third sort key of the plan: block in the next round (nb values) or off (1)
   bool use_xch = false;  // sharded cells: block steps exchanged through peer memory (one cooperative launch per call)
@@ -305,10 +303,12 @@ struct hb_handle {
   size_t pt_cap = 0;
   DevBuf<float> remT;    // [2][nb][J][KS] next round's removal sums per (block, tuple)
   DevBuf<int> next_at, chunk_q0, chunk_nq;
+  DevBuf<int> lvl_ptr, lvl_tup;  // CSR level -> tuples (+ one trailing word: B_vec[0])
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
   int trace_cap = 0;
   std::vector<int> tuple_levels_h;  // [J][C]
   std::vector<int> sort_perm_h;
+  std::vector<int64_t> kmeans_cells;  // global cells chosen by the native initialize_centroids (test hook)
 
   // traces (harmony.h:55-56); values are produced on the device and pulled lazily
   int obj_count = 0;                      // objective evaluations so far (device slots)
@@ -541,8 +541,8 @@ int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_o
     if (plan_mode) {
       // O, E of the assignment = the sums of the blocks' removal terms (harmony.cpp:226-227)
       const size_t XH = (size_t)B * KS + KS;
-      if (h->world > 1)
-        for (int j = 0; j < h->nb; ++j) TRY(allreduce_f(h, h->acc2.p + (size_t)(j + 1) * 2 * XH + XH, XH));
+      // sharded cells: the rem halves of slots 1 .. nb in ONE all-reduce (their add halves are still zero here)
+      if (h->world > 1) TRY(allreduce_f(h, h->acc2.p + 2 * XH, 2 * XH * (size_t)h->nb));
       k_assign_finalize_plan<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->acc2.p, h->nb, h->Pr_b.p, h->O.p, h->E.p, B, K, KS);
       CKL();
       h->zc_pending_norm = normalise;  // the normalised embedding (harmony.cpp:220) is materialised on demand
@@ -819,11 +819,9 @@ void release_peer_exchange(hb_handle* h) {
   }
   h->use_xch = false;
 }
-float* xch_inbox(const XchArea* a, void* base) { return reinterpret_cast<float*>(base); }
-unsigned* xch_flags(const XchArea* a, void* base) { return reinterpret_cast<unsigned*>(reinterpret_cast<float*>(base) + a->slots * a->world * a->XH); }
-float* xch_remT(const XchArea* a, void* base) {
-  return reinterpret_cast<float*>(base) + a->slots * a->world * a->XH + ((a->slots * a->world + 3) & ~(size_t)3);
-}
+// layout of an area (floats): inbox [slots][world][XH] of 8-byte (value, epoch) words | remT [2][nb][J][KS]
+uint2* xch_inbox(const XchArea* a, void* base) { return reinterpret_cast<uint2*>(base); }
+float* xch_remT(const XchArea* a, void* base) { return reinterpret_cast<float*>(base) + 2 * a->slots * a->world * a->XH; }
 // Collective over the handle's communicator.  Leases an area all ranks have free, or creates a new one:
 // allocates this rank's part, exchanges the IPC handles and maps the other ranks' parts.  If any rank cannot
 // map a peer the exchange stays off on all ranks (the update then runs one launch + all-reduce per block step).
@@ -911,11 +909,9 @@ int setup_peer_exchange(hb_handle* h, int Tplan) {
   for (int r = 0; r < W; ++r) {
     void* b = (r == h->rank) ? (void*)area->base : area->peer[r];
     x.peer_inbox[r] = xch_inbox(area, b);
-    x.peer_flags[r] = xch_flags(area, b);
     x.peer_remT[r] = xch_remT(area, b);
   }
   x.inbox = x.peer_inbox[h->rank];
-  x.flags = x.peer_flags[h->rank];
   h->use_xch = true;
   return 0;
 }
@@ -985,6 +981,9 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.next_at = h->next_at.p + R0 * h->n;
   a.ranges = h->ranges.p + R0 * h->nb * h->coop_grid;
   a.tuple_levels = h->tuple_levels.p;
+  a.lvl_ptr = h->lvl_ptr.p;
+  a.lvl_tup = h->lvl_tup.p;
+  a.lvl_first1 = h->lvl_ptr.p + h->B + 1;
   a.sigma = h->sigma.p;
   a.theta = h->theta.p;
   a.Pr_b = h->Pr_b.p;
@@ -1007,7 +1006,6 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.has_next_from = T - 1;
   a.sigma_uniform = h->sigma_uniform ? 1 : 0;
   a.sigma0 = h->sigma0;
-  a.nbatch = h->u4_nbatch;
   a.ring_rows = h->u5_ring_rows;
   {
     static const int flags = getenv("HB_U5_FLAGS") ? atoi(getenv("HB_U5_FLAGS")) : 0;
@@ -1052,24 +1050,6 @@ int upd_launch(hb_handle* h, UpdArgs a, bool cooperative) {
   });
 }
 template <int NV, bool SIGU>
-int upd4_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
-  const size_t smem = upd4_smem_bytes(NV, a.nbatch, a.KS);
-  CK(cudaFuncSetAttribute(k_update_steps4<NV, SIGU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  a.coop = cooperative ? 1 : 0;
-  Upd4Launch lp;
-  lp.a = a;
-  if (h->use_xch) lp.x = h->xch;
-  if (cooperative) {
-    void* args[] = {&lp};
-    CK(cudaLaunchCooperativeKernel((void*)k_update_steps4<NV, SIGU>, dim3(h->coop_grid), dim3(U4_THREADS), args, smem,
-                                   h->stream));
-  } else {
-    k_update_steps4<NV, SIGU><<<h->coop_grid, U4_THREADS, smem, h->stream>>>(lp);
-  }
-  CKL();
-  return 0;
-}
-template <int NV, bool SIGU>
 int upd5_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
   const size_t smem = upd5_smem_bytes(NV, a.ring_rows, a.KS);
   CK(cudaFuncSetAttribute(k_update_steps5<NV, SIGU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1089,15 +1069,9 @@ int upd5_launch_nv(hb_handle* h, Upd4Args& a, bool cooperative) {
 }
 int upd4_launch(hb_handle* h, Upd4Args a, bool cooperative) {
   const bool su = h->sigma_uniform;  // the default: scalar sigma (objective terms simplify)
-  if (h->use_v5) {
-    switch (upd4_nv(h->KS)) {
-      case 1: return su ? upd5_launch_nv<1, true>(h, a, cooperative) : upd5_launch_nv<1, false>(h, a, cooperative);
-      case 2: return su ? upd5_launch_nv<2, true>(h, a, cooperative) : upd5_launch_nv<2, false>(h, a, cooperative);
-    }
-  }
   switch (upd4_nv(h->KS)) {
-    case 1: return su ? upd4_launch_nv<1, true>(h, a, cooperative) : upd4_launch_nv<1, false>(h, a, cooperative);
-    case 2: return su ? upd4_launch_nv<2, true>(h, a, cooperative) : upd4_launch_nv<2, false>(h, a, cooperative);
+    case 1: return su ? upd5_launch_nv<1, true>(h, a, cooperative) : upd5_launch_nv<1, false>(h, a, cooperative);
+    case 2: return su ? upd5_launch_nv<2, true>(h, a, cooperative) : upd5_launch_nv<2, false>(h, a, cooperative);
   }
   return fail(h, 2, "K = %d is not supported by the persistent update kernel", h->K);
 }
@@ -1138,8 +1112,7 @@ int run_update_v4(hb_handle* h, int T, int t0, int t1, bool rem_ready) {
     k_rem_sums<<<dim3(h->coop_grid, nb), 256, sizeof(float) * 8 * (size_t)h->KS, h->stream>>>(
         h->R.p, a.order, a.ranges, a.tuple_levels, a.acc, 0, h->coop_grid, h->K, h->KS, h->C, h->B);
     CKL();
-    if (h->world > 1)
-      for (int j = 0; j < nb; ++j) TRY(allreduce_f(h, h->acc2.p + (size_t)(j + 1) * SL + XH, XH));
+    if (h->world > 1) TRY(allreduce_f(h, h->acc2.p + SL, SL * (size_t)nb));  // rem halves of slots 1 .. nb (add halves: zero)
   }
   if (h->world <= 1 || h->use_xch) {
     a.s_begin = t0 * nb;
@@ -1165,7 +1138,7 @@ int run_update_v4(hb_handle* h, int T, int t0, int t1, bool rem_ready) {
     }
     TRY(allreduce_f(h, h->acc2.p + (size_t)(t1 * nb + 1) * SL, XH));  // add_{S-1}
   }
-  if (h->dbg_cta >= 0 && h->world <= 1) dump_step_trace(h, (t1 - t0) * nb, 8);
+  if (h->dbg_cta >= 0 && h->rank == 0) dump_step_trace(h, (t1 - t0) * nb, 8);
   {
     RegionScope r4(h, "k_update_finalize");
     k_update_finalize4<<<grid_for(BK, 256, 64), 256, 0, h->stream>>>(a, h->use_xch ? h->xch : Upd4Xch{}, t1 * nb, h->O.p, h->E.p);
@@ -1853,10 +1826,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   const bool force_v1 = getenv("HB_UPDATE_V1") != nullptr, force_v2 = getenv("HB_UPDATE_V2") != nullptr;
   h->coop_grid = h->num_sms;  // one persistent CTA per SM
   h->aligned_ranges = (2 * J <= h->coop_grid);
-  h->u4_nbatch = upd4_nbatch(KS, smem_limit);
-  h->use_v4 = !force_v1 && !force_v2 && h->aligned_ranges && h->u4_nbatch > 0;
   h->u5_ring_rows = upd5_ring_rows(KS, smem_limit);
-  h->use_v5 = h->use_v4 && h->u5_ring_rows > 0 && (uint64_t)N * (uint64_t)KS < (1ull << 32) && getenv("HB_UPDATE_V4") == nullptr;
+  h->use_v4 = !force_v1 && !force_v2 && h->aligned_ranges && h->u5_ring_rows > 0 && (uint64_t)N * (uint64_t)KS < (1ull << 32);
   h->use_v2 = h->use_v4 || (!force_v1 && (KS <= 256) && (J <= 8192) && upd_smem_bytes(h) <= smem_limit);
   h->plan_nsub = (h->use_v4 && h->nb <= 64) ? h->nb : 1;
   h->plan_rounds = Tplan;
@@ -1965,6 +1936,20 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   UP(sort_perm, h->sort_perm_h);
   UP(inv_sort, inv_sort);
   UP(tuple_levels, h->tuple_levels_h);
+  // CSR level -> tuples containing it, ascending tuple order; trailing word: the number of levels of covariate 0
+  std::vector<int> lvl_ptr_h(B + 2, 0), lvl_tup_h((size_t)J * C);
+  {
+    for (size_t i = 0; i < h->tuple_levels_h.size(); ++i) lvl_ptr_h[h->tuple_levels_h[i] + 1]++;
+    for (int b = 0; b < B; ++b) lvl_ptr_h[b + 1] += lvl_ptr_h[b];
+    std::vector<int> fill(lvl_ptr_h.begin(), lvl_ptr_h.begin() + B);
+    for (int q = 0; q < J; ++q)
+      for (int c = 0; c < C; ++c) lvl_tup_h[fill[h->tuple_levels_h[(size_t)q * C + c]]++] = q;
+    lvl_ptr_h[B + 1] = h->B_vec[0];
+    CK(h->lvl_ptr.alloc(B + 2));
+    CK(h->lvl_tup.alloc(std::max<size_t>(1, lvl_tup_h.size())));
+    UP(lvl_ptr, lvl_ptr_h);
+    UP(lvl_tup, lvl_tup_h);
+  }
   UP(cov_of_d, h->cov_of);
   UP(tile_cell0, t_cell0);
   UP(tile_len, t_len);
@@ -2020,18 +2005,72 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
     // Y = normalise(kmeans_centers(..)) (harmony.cpp:133-136), centroids injected by the caller
     TRY(upload_small(h, Y0, (size_t)h->K * h->d, h->Y.p));
   } else {
-    // native initialisation: K distinct random cells, then 10 Lloyd iterations (utils.cpp:53-64 runs
-    // 10 x arma::kmeans(.., keep_existing, 1)) on the cosine-normalised cells, sharded like everything else
+    // native kmeans_centers (utils.cpp:10-64) on the cosine-normalised cells, sharded like everything else:
+    // initialize_centroids' rule (K start cells, then per centroid the winner of an exponential race weighted by the
+    // distance from its start cell, already-taken cells skipped) with keyed-hash uniforms, then 10 Lloyd iterations
+    // (10 x arma::kmeans(.., keep_existing, 1): Euclidean assignment, means of the members).
     const int K = h->K, d = h->d;
     const size_t Kd = (size_t)K * d;
+    if (h->N_global >= (1ll << 32)) return fail(h, 2, "native k-means initialisation supports < 2^32 cells; pass Y0");
     DevBuf<float> ysum;
     CK(ysum.alloc(Kd + K));
-    CK(cudaMemsetAsync(h->Y.p, 0, sizeof(float) * Kd, h->stream));
-    const uint64_t key = hb_mix64(h->seed ^ 0x6b6d65616e73ull);
-    k_kmeans_seed<<<K, 64, 0, h->stream>>>(h->Zc.p, h->inv_sort.p, h->Y.p, K, d, h->DS, h->N_global, h->cell_offset, h->n,
-                                            h->half_bits, key);
-    CKL();
-    TRY(allreduce_f(h, h->Y.p, Kd));
+    const uint64_t seed = hb_mix64(h->seed ^ 0x6b6d65616e73ull);
+    DevBuf<int64_t> cells_d;
+    DevBuf<unsigned long long> best_d;
+    CK(cells_d.alloc(K));
+    CK(best_d.alloc(K));
+    std::vector<int64_t> cells(K);
+    auto gather = [&](int only) -> int {  // Y rows <- cells (all, or one centroid), summed over the ranks that own them
+      CK(cudaMemcpyAsync(cells_d.p, cells.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, h->stream));
+      float* dst = (only >= 0) ? h->Y.p + (size_t)only * d : h->Y.p;
+      const size_t cnt = (only >= 0) ? (size_t)d : Kd;
+      CK(cudaMemsetAsync(dst, 0, sizeof(float) * cnt, h->stream));
+      k_kmeans_gather<<<K, 64, 0, h->stream>>>(h->Zc.p, h->inv_sort.p, h->Y.p, cells_d.p, K, d, h->DS, h->cell_offset, h->n, only);
+      CKL();
+      return allreduce_f(h, dst, cnt);
+    };
+    // (1) start cells: floor(u (N - 1))  (utils.cpp:12-16)
+    for (int k = 0; k < K; ++k)
+      cells[k] = (int64_t)std::floor((double)kmeans_uniform(seed, (uint64_t)K, (uint64_t)k) * (double)(h->N_global - 1));
+    TRY(gather(-1));
+    // (2) the races of all centroids in one pass over the cells (a centroid's race only looks at its own start cell)
+    const size_t smem_pp = sizeof(float) * Kd;
+    if (smem_pp > 200 * 1024) return fail(h, 2, "K*d too large for the native k-means initialisation; pass Y0");
+    CK(cudaFuncSetAttribute(k_kmeans_race, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pp));
+    std::vector<unsigned long long> best(K);
+    auto race = [&](int i0, int i1, const std::vector<int64_t>& taken) -> int {
+      DevBuf<int64_t> taken_d;
+      if (!taken.empty()) {
+        CK(taken_d.alloc(taken.size()));
+        CK(cudaMemcpyAsync(taken_d.p, taken.data(), sizeof(int64_t) * taken.size(), cudaMemcpyHostToDevice, h->stream));
+      }
+      CK(cudaMemsetAsync(best_d.p + i0, 0xff, sizeof(unsigned long long) * (i1 - i0), h->stream));
+      k_kmeans_race<<<grid_for(h->n, 128, h->num_sms * 4), 128, sizeof(float) * (size_t)(i1 - i0) * d, h->stream>>>(
+          h->Zc.p, h->sort_perm.p, h->Y.p, best_d.p, taken.empty() ? nullptr : taken_d.p, (int)taken.size(), h->n, K, d, h->DS,
+          h->cell_offset, seed, i0, i1);
+      CKL();
+      if (h->world > 1) CKN(g_nccl.AllReduce(best_d.p + i0, best_d.p + i0, (size_t)(i1 - i0), ncclUint64, ncclMin, h->comm, h->stream));
+      CK(cudaMemcpyAsync(best.data() + i0, best_d.p + i0, sizeof(unsigned long long) * (i1 - i0), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      return 0;
+    };
+    TRY(race(0, K, {}));
+    // (3) accept in centroid order; a winner that is already taken re-runs that centroid's race without the taken cells
+    // (utils.cpp:38-45); the race of centroid i reads its START cell, so Y is only rewritten afterwards
+    std::vector<int64_t> taken;
+    for (int i = 0; i < K; ++i) {
+      int64_t w = (int64_t)(best[i] & 0xffffffffull);
+      if (best[i] == ~0ull) return fail(h, 3, "native k-means initialisation: no free cell for centroid %d", i);
+      if (std::find(taken.begin(), taken.end(), w) != taken.end()) {
+        TRY(race(i, i + 1, taken));
+        if (best[i] == ~0ull) return fail(h, 3, "native k-means initialisation: no free cell for centroid %d", i);
+        w = (int64_t)(best[i] & 0xffffffffull);
+      }
+      taken.push_back(w);
+      cells[i] = w;
+    }
+    h->kmeans_cells = cells;
+    TRY(gather(-1));
     const size_t smem = sizeof(float) * Kd;
     if (smem > 200 * 1024) return fail(h, 2, "K*d too large for the native k-means initialisation; pass Y0");
     CK(cudaFuncSetAttribute(k_kmeans_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2520,16 +2559,27 @@ int hb_debug_widen(double* out, const float* in, int64_t n, int threads) {
 }
 
 // Ring geometry of the persistent update kernel for rows of KS floats (test hook, host only):
-// out = {float4 per lane, ring slots, rows per slot, shared-memory bytes}; 0 if the kernel cannot run the shape.
+// out = {float4 per lane, groups per warp ring, rows per group, shared-memory bytes, warps}; 0 if the kernel cannot run the shape.
 int hb_debug_update_geometry(int KS, int nb, int64_t out[9]) {
   (void)nb;
   if (KS <= 0 || (KS & 3)) return 0;
-  const int nbt = upd4_nbatch(KS, (size_t)227 * 1024 - 256);
-  if (nbt <= 0) return 0;
-  const int nv = upd4_nv(KS);
-  const int64_t v[9] = {nv, nbt, U4_BR, (int64_t)upd4_smem_bytes(nv, nbt, KS), U4_NP, U4_NW, U4_MINBATCH, 0, 0};
+  const int D = upd5_ring_rows(KS, (size_t)227 * 1024 - 256);
+  if (D <= 0) return 0;
+  const int nv = upd4_nv(KS), ru = upd5_ru(nv);
+  const int64_t v[9] = {nv, D / ru, ru, (int64_t)upd5_smem_bytes(nv, D, KS), U5_NW, 0, 0, 0, 0};
   for (int i = 0; i < 9; ++i) out[i] = v[i];
   return 1;
+}
+
+// Test hooks of the native kmeans_centers: the uniform of (centroid i, global cell g) under the handle's seed, and
+// the cells initialize_centroids chose (K values; 0 if the native initialisation has not run).
+double hb_debug_kmeans_uniform(const hb_handle* h, uint64_t i, uint64_t g) {
+  return (double)kmeans_uniform(hb_mix64(h->seed ^ 0x6b6d65616e73ull), i, g);
+}
+int hb_debug_kmeans_cells(const hb_handle* h, int64_t* out) {
+  if (!h || h->kmeans_cells.empty()) return 0;
+  for (size_t i = 0; i < h->kmeans_cells.size(); ++i) out[i] = h->kmeans_cells[i];
+  return (int)h->kmeans_cells.size();
 }
 
 int hb_enable_timing(hb_handle* h, int on) {

@@ -108,18 +108,64 @@ __global__ void k_normalise_rows(const float* __restrict__ src, float* __restric
 // ------------------------------------------------------------------------------------------------
 // native k-means initialisation (stand-in for kmeans_centers, utils.cpp:10-64; outside the timed loop)
 // ------------------------------------------------------------------------------------------------
-// seeds: centroid k <- the (cosine-normalised) cell at position k of a keyed random permutation of the
-// GLOBAL cell indices (distinct by construction); each rank writes the seeds it owns, the rest stay 0.
-__global__ void k_kmeans_seed(const float* __restrict__ Zc, const int* __restrict__ inv_sort, float* __restrict__ Y,
-                              int K, int d, int DS, int64_t N_global, int64_t cell_offset, int64_t n_local,
-                              int half_bits, uint64_t key) {
-  int k = blockIdx.x;
-  if (k >= K) return;
-  int64_t g = (int64_t)hb_permute_inv((uint64_t)k, (uint64_t)N_global, half_bits, key);
-  int64_t l = g - cell_offset;
+// initialize_centroids (utils.cpp:10-49).  The reference draws K start cells floor(u N'), N' = N - 1, and then,
+// for every centroid i in turn, replaces it by the cell j that minimises -log(u_ij) / |2 (1 - y_i . x_j)| (a race of
+// exponentials: cell j wins with probability proportional to its distance from the START cell i), skipping cells
+// that were already taken.  R's random stream cannot be replayed; here u is a keyed hash of (seed, i, global cell),
+// so the rule itself is the reference's and tests replay it exactly (tests/numpy_restatement.py).
+__host__ __device__ __forceinline__ float kmeans_uniform(uint64_t seed, uint64_t i, uint64_t g) {
+  const uint64_t h = hb_mix64(seed ^ hb_mix64((i << 40) ^ g ^ 0x6b6d2b2b00000000ull));
+  return ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // 24 random bits, strictly inside (0, 1)
+}
+// Y[k] <- the (cosine-normalised) cell with GLOBAL index cells[k]; each rank writes the rows it owns, the rest
+// stay 0 (the caller zeroes Y and all-reduces it).  only >= 0: just that centroid.
+__global__ void k_kmeans_gather(const float* __restrict__ Zc, const int* __restrict__ inv_sort, float* __restrict__ Y,
+                                const int64_t* __restrict__ cells, int K, int d, int DS, int64_t cell_offset,
+                                int64_t n_local, int only) {
+  const int k = blockIdx.x;
+  if (k >= K || (only >= 0 && k != only)) return;
+  const int64_t l = cells[k] - cell_offset;
   if (l < 0 || l >= n_local) return;
   const float* z = Zc + (size_t)inv_sort[l] * DS;
   for (int c = threadIdx.x; c < d; c += blockDim.x) Y[(size_t)k * d + c] = z[c];
+}
+// One pass over the local cells: best[i] = min over cells of (float bits of -log(u_ij) / dist_ij) << 32 | global cell
+// for the centroids i in [i0, i1) (all values are >= 0, so the bit patterns order like the floats; ties go to the
+// smaller cell index).  Cells listed in `taken` (ntaken global indices) do not take part.  Thread per cell, start
+// centroids in shared memory.
+__global__ void __launch_bounds__(128) k_kmeans_race(const float* __restrict__ Zc, const int* __restrict__ sort_perm,
+                                                     const float* __restrict__ Y, unsigned long long* __restrict__ best,
+                                                     const int64_t* __restrict__ taken, int ntaken, int64_t n, int K, int d,
+                                                     int DS, int64_t cell_offset, uint64_t seed, int i0, int i1) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ys = smem;  // [i1 - i0][d]
+  for (int i = threadIdx.x; i < (i1 - i0) * d; i += blockDim.x) Ys[i] = Y[(size_t)i0 * d + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x; base < n; base += stride) {  // whole warps stay in the loop
+    const int64_t s = base + threadIdx.x;
+    const bool on = s < n;
+    const float* z = Zc + (size_t)(on ? s : 0) * DS;
+    const uint64_t g = (uint64_t)(cell_offset + (on ? sort_perm[s] : 0));
+    bool free_cell = on;
+    for (int e = 0; e < ntaken && free_cell; ++e) free_cell = (uint64_t)taken[e] != g;
+    for (int i = i0; i < i1; ++i) {
+      const float* y = Ys + (size_t)(i - i0) * d;
+      float acc = 0.f;
+      for (int c = 0; c < d; ++c) acc = fmaf(z[c], y[c], acc);
+      const float dist = fabsf(2.f * (1.f - acc));
+      const float p = -logf(kmeans_uniform(seed, (uint64_t)i, g)) / dist;  // dist == 0: +inf, never the minimum
+      unsigned long long key = free_cell ? (((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(g & 0xffffffffull))
+                                         : 0xffffffffffffffffull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other < key ? other : key;
+      }
+      if (lane == 0 && key != 0xffffffffffffffffull) atomicMin(best + i, key);
+    }
+  }
 }
 // one Lloyd assignment pass on the cosine-normalised cells: nearest centroid by largest dot product,
 // accumulate per-cluster sums and counts.  Thread per cell, centroids in shared memory.

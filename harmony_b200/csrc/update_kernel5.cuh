@@ -281,27 +281,15 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
     if (sh_last) {
       const float* src = a.acc + (size_t)sl * SL;  // complete: every CTA's atomics preceded its count
       const size_t entry = (size_t)sl * x.world + x.rank;
-      for (int r = 0; r < x.world; ++r) {
-        float* dst = x.peer_inbox[r] + entry * x.XH;
-        for (int i = tid * 4; i < x.XH; i += U5_THREADS * 4)
-          *reinterpret_cast<float4*>(dst + i) = __ldcg(reinterpret_cast<const float4*>(src + i));
+      for (int i = tid; i < x.XH; i += U5_THREADS) {
+        const float v = __ldcg(src + i);
+        for (int r = 0; r < x.world; ++r) u4_st_ll(x.peer_inbox[r] + entry * x.XH + i, v, x.epoch);
       }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < x.world) u4_st_release_sys(x.peer_flags[tid] + entry, x.epoch);
     }
   };
   auto wait_for = [&](const unsigned* c) {
     if (tid == 0) {
       while (u4_ld_acquire_gpu(c) < (unsigned)grid) __nanosleep(20);
-      __threadfence();
-    }
-    __syncthreads();
-  };
-  auto wait_slot = [&](int sl) {
-    if (tid < x.world) {
-      const unsigned* f = x.flags + (size_t)sl * x.world + tid;
-      while (u4_ld_acquire_sys(f) != x.epoch) __nanosleep(40);
       __threadfence();
     }
     __syncthreads();
@@ -325,34 +313,8 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
     return tv;
   };
   auto fold_round = [&](int t) {
-    const size_t par_off = (size_t)(t & 1) * nb * J * KS;
-    float* Tz = a.remT + (size_t)((t + 1) & 1) * nb * J * KS;
-    for (int item = cta * U5_THREADS + tid; item < nb * K; item += grid * U5_THREADS) {
-      const int j = item / K, k = item - j * K;
-      const size_t joff = par_off + (size_t)j * J * KS + k;
-      float* slot = a.acc + (size_t)(t * nb + j + 1) * SL;
-      float* rem_O = slot + BK + KS;
-      float* rem_rs = rem_O + BK;
-      float rs = 0.f;
-      for (int q = 0; q < J; ++q) {
-        float v;
-        if (multi) {
-          v = 0.f;
-          for (int r = 0; r < x.world; ++r) v += __ldcg(x.peer_remT[r] + joff + (size_t)q * KS);
-        } else {
-          v = __ldcg(a.remT + joff + (size_t)q * KS);
-        }
-        if (v != 0.f) {
-          rs += v;
-          for (int c = 0; c < C; ++c) {
-            float* o = rem_O + (size_t)__ldg(a.tuple_levels + q * C + c) * KS + k;
-            *o = *o + v;
-          }
-        }
-        Tz[((size_t)j * J + q) * KS + k] = 0.f;
-      }
-      rem_rs[k] = rs;
-    }
+    for (int item = cta * U5_THREADS + tid; item < nb * K; item += grid * U5_THREADS)
+      u4_fold_column(a, multi ? &x : nullptr, t, item / K, item % K);
   };
 
   // objective partial sums of this lane.  Scalar sigma: accA = sum_rows (1/s) sum_k e u, accB = sum_rows (1/s) sum_k e log Psum
@@ -396,7 +358,7 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
     const bool has_next = t < a.has_next_from && !(a.dbg_flags & 1);
     if (a.coop) {
       if (s > a.s_begin) wait_for(cntU + s - 1);  // add_{s-1}, ring(s-1); at j == 0 also: round t-1 is complete
-      if (multi && s >= 1) wait_slot(s + 1);      // ... on every rank: add_{s-1} lives in slot(s) = index s + 1
+      stamp(s, 7);
       if (j == 0 && t > 0) {
         fold_round(t);
         signal(cntF + t, -1);

@@ -4,6 +4,7 @@ Only argument preparation lives here (the reference does it in R too); all arith
 cell matrices happens behind the C ABI (include/harmony_b200.h) in hand-written CUDA.
 """
 import math
+import os
 import sys
 
 import numpy as np
@@ -129,8 +130,9 @@ def RunHarmony(data_mat, meta_data, vars_use=None, theta=None, sigma=0.1, lambda
     obj.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], a["max_iter_kmeans"],
               a["epsilon_kmeans"], a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"],
               a["batch_proportion_cutoff"], verbose)
-    if seed is not None:
-        obj.set_seed(seed)
+    if seed is None:   # R without set.seed(): the session's random stream differs from run to run
+        seed = int.from_bytes(os.urandom(8), "little")
+    obj.set_seed(seed)
     if verbose:
         print("Initializing state using k-means centroids initialization", file=sys.stderr)
     obj.init_cluster_cpp()

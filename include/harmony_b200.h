@@ -151,10 +151,14 @@ uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse);
 /* Test hook (host only): the host worker pool of the threaded download path (HB_DOWNLOAD_MT=1) widens n floats to
  * doubles; `threads` sizes the pool on first use (<= 0: HB_HOST_THREADS or the core count).  Returns the pool size. */
 int hb_debug_widen(double* out, const float* in, int64_t n, int threads);
+/* Test hooks of the native kmeans_centers (hb_init_cluster(h, NULL); utils.cpp:10-64): the keyed-hash uniform that
+ * stands in for arma::randu at (centroid i, global cell g) — i = K addresses the K start-cell draws — and the global
+ * cells initialize_centroids chose (returns their number, 0 if the native initialisation has not run). */
+double hb_debug_kmeans_uniform(const hb_handle* h, uint64_t i, uint64_t g);
+int hb_debug_kmeans_cells(const hb_handle* h, int64_t* out);
 /* Test hook (host only): ring geometry of the persistent update_R kernel for rows of KS floats:
- * out = {float4 per lane, ring slots, rows per slot, shared-memory bytes, producer warps, consumer warps, cp.async
- * smallest ring (slots), 0, 0}.  Returns 1 if the shape is supported, 0 if the library would use the
- * per-step kernels. */
+ * out = {float4 per lane, row groups per warp ring (a power of two), rows per group, shared-memory bytes, warps per
+ * CTA, 0, 0, 0, 0}.  Returns 1 if the shape is supported, 0 if the library would use the other update kernels. */
 int hb_debug_update_geometry(int KS, int nb, int64_t out[9]);
 
 #ifdef __cplusplus

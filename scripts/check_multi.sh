@@ -24,3 +24,6 @@ for n in ("${N}gpu_xch", "${N}gpu_nccl", "1gpu_ref"):
     except Exception as e:
         print(n, "failed:", e)
 PY
+HB_TRACE_STEPS=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 \
+    bench.py --gpus $N --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+cp gpurun_out/step_trace.txt gpurun_out/step_trace_${N}gpu.txt

@@ -148,8 +148,8 @@ def test_native_update_order_is_a_permutation(n):
 
 def test_update_kernel_ring_geometry():
     """Ring geometry of the persistent update kernel: for every padded row width the library either declines
-    (the per-step kernels serve the shape) or returns a ring that fits shared memory, whose lanes cover the row and
-    whose slots split evenly among the producer warps with room for their unpublished batches."""
+    (the other update kernels serve the shape) or returns per-warp rings that fit shared memory, whose lanes cover
+    the row and whose depth is a power of two (slot index = group counter & (depth - 1))."""
     import ctypes
     L = _lib.lib()
     out = (ctypes.c_int64 * 9)()
@@ -158,12 +158,12 @@ def test_update_kernel_ring_geometry():
         if not L.hb_debug_update_geometry(KS, 20, out):
             continue
         supported += 1
-        NV, nbatch, BR, smem, NP, NW, minb = list(out)[:7]
+        NV, DG, RU, smem, NW = list(out)[:5]
         assert NV in (1, 2) and 128 * NV >= KS and (NV == 1 or 128 < KS)   # lane l owns float4 l + 32 v
-        assert nbatch % NP == 0 and nbatch >= minb
-        assert smem <= 227 * 1024 - 256 and smem >= nbatch * BR * KS * 4
+        assert DG >= 2 and DG & (DG - 1) == 0 and RU in (2, 4) and NW == 16
+        assert smem <= 227 * 1024 - 256 and smem >= NW * DG * RU * KS * 4
     assert not L.hb_debug_update_geometry(6, 20, out)          # row widths are multiples of 4 floats
-    assert L.hb_debug_update_geometry(100, 20, out) and out[0] == 1 and out[1] * out[2] >= 400   # K = 100: > 1 block step of rows
+    assert L.hb_debug_update_geometry(100, 20, out) and out[0] == 1 and out[1] * out[2] >= 24   # K = 100: > 1 block step of a warp's rows at 1M cells
     assert L.hb_debug_update_geometry(200, 20, out) and out[0] == 2
     assert supported >= 50
 
