@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--cells-per-gpu", type=int, default=0, help="override the workload's shard size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-set", type=int, default=0, help="HB_KERNEL_SET test hook of the library (A/B runs only)")
     ap.add_argument("--ref-cells", type=int, default=0, help="cells of the bounded CPU sample (--impl reference); 0 = by workload")
     args = ap.parse_args()
     W.clear()
@@ -331,6 +332,8 @@ def main():
 
     def make_obj():
         g = harmony(device=local_rank, comm=new_comm())
+        if args.kernel_set:
+            g.kernel_set = args.kernel_set
         g.setup(Z, kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, kw["B_vec"],
                 kw["cutoff"])
         g.set_seed(1234)
@@ -471,7 +474,7 @@ def main():
                                        f"{W['B_vec']}), K={K}, T={T}, block_size=0.05 ({W['name']})",
                            "config_id": args.config,
                            "cells_per_gpu": n_local, "parallelism": f"cells sharded x{world}",
-                           "switches": sorted(k for k in os.environ if k.startswith("HB_")),  # experimental paths, if any
+                           "switches": sorted(k for k in os.environ if k.startswith("HB_")) + ([f"kernel_set={args.kernel_set}"] if args.kernel_set else []),
                            "l2": f"state (U,R,Z = {n_local * (2 * KS + 2 * DS) * 4 / 1e9:.1f} GB per GPU) is far larger than the 126 MB L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline,

@@ -31,10 +31,8 @@
 #include "update_kernel4.cuh"
 #include "update_kernel5.cuh"
 #include "assign_tc3.cuh"
-#include "apply_tc.cuh"
-#include "apply_tc2.cuh"
-#include "stats_tc.cuh"
-#include "stats_tc2.cuh"
+#include "apply_tc3.cuh"
+#include "stats_tc3.cuh"
 
 namespace {
 
@@ -287,6 +285,7 @@ struct hb_handle {
   DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
   int tc_ntiles = 0;
   bool use_tc_assign = false, use_tc_apply = false, use_tc_stats = false;
+  int kernel_set = 0;            // HB_KERNEL_SET test hook (bits HB_KS_*), read by hb_setup
   bool legacy_centroid = false;  // HB_LEGACY_CENTROID_STEP: centroid update at the top of every clustering round
   DevBuf<float> Rkeep, OEkeep;   // R / O,E saved around the distance-only assignment of that step
   DevBuf<double> objkeep;
@@ -698,7 +697,7 @@ int plan_sort(hb_handle* h, int t, int nt, bool last_has_next, int set, cudaStre
                                                                        seg_start, tile_base);
   CKL();
   if (h->use_v2 && h->aligned_ranges) {
-    k_plan_ranges<<<dim3((nb * h->coop_grid + 127) / 128, nt), 128, 0, st>>>(seg_start, nb, J, h->coop_grid,
+    k_plan_ranges<<<dim3(nb, nt), 256, 0, st>>>(seg_start, nb, J, h->coop_grid,
                                                                             h->ranges.p + (R0 + t) * nb * h->coop_grid);
     CKL();
   }
@@ -1007,10 +1006,7 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.sigma_uniform = h->sigma_uniform ? 1 : 0;
   a.sigma0 = h->sigma0;
   a.ring_rows = h->u5_ring_rows;
-  {
-    static const int flags = getenv("HB_U5_FLAGS") ? atoi(getenv("HB_U5_FLAGS")) : 0;
-    a.dbg_flags = flags;
-  }
+  a.dbg_flags = 0;
   a.coop = 1;
   a.dbg = (h->dbg_cta >= 0) ? h->dbg.p : nullptr;
   a.dbg_cta = h->dbg_cta;
@@ -1210,16 +1206,9 @@ int run_correct(hb_handle* h) {
       t.DS = h->DS;
       t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
       const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
-      static const bool stats_v2 = getenv("HB_STATS_V2") != nullptr;  // experimental 3-stage variant
-      if (stats_v2 && stats_tc2_smem_bytes(h->KS, h->DS) <= 227 * 1024) {
-        const size_t smem_tc = stats_tc2_smem_bytes(h->KS, h->DS);
-        CK(cudaFuncSetAttribute(k_stats_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-        k_stats_tc2<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
-      } else {
-        const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
-        CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-        k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
-      }
+      const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
+      CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+      k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
       CKL();
     } else {
     StatsArgs a;
@@ -1301,25 +1290,20 @@ int run_correct(hb_handle* h) {
       a.dbg = h->dbg.p;
     }
     const int grid = (h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    static const bool apply_v2 = getenv("HB_APPLY_V2") != nullptr;  // experimental deeper-ring variant
-    if (apply_v2 && apply_tc2_smem_bytes(a.KD, h->KS) <= 227 * 1024) {
-      const size_t smem = apply_tc2_smem_bytes(a.KD, h->KS);
-      CK(cudaFuncSetAttribute(k_apply_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_apply_tc2<<<grid, AP_THREADS, smem, h->stream>>>(a);
-    } else {
+    {
       const size_t smem = apply_tc_smem_bytes(a.KD, h->KS);
       CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
     }
     CKL();
     if (tracing) {
-      std::vector<long long> st(64 * 12);
+      std::vector<long long> st(32 * 16);
       CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       if (FILE* f = fopen("gpurun_out/apply_trace.txt", "w")) {
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < 32; ++i) {
           fprintf(f, "%d", i);
-          for (int k = 0; k < 12; ++k) fprintf(f, " %lld", st[(size_t)i * 12 + k]);
+          for (int k = 0; k < 16; ++k) fprintf(f, " %lld", st[(size_t)i * 16 + k] ? st[(size_t)i * 16 + k] - st[0] : -1);
           fprintf(f, "\n");
         }
         fclose(f);
@@ -1371,23 +1355,32 @@ int check_err_flag(hb_handle* h) {
   return 0;
 }
 
-// rows of a per-cell field (device row stride ld), un-sorted and widened to double, via a bounded staging buffer
-// Threaded variant (HB_DOWNLOAD_MT=1): rows are gathered on the device as floats (half the PCIe bytes), DMA'd
-// into two pinned staging buffers and widened into the caller's array by the host pool while the next chunk is
-// in flight.  The pinned buffers live for the life of the process.
+// rows of a per-cell field (device row stride ld), un-sorted and widened to double.  Rows are gathered on the device
+// as floats (half the PCIe bytes), DMA'd into two pinned staging buffers and widened into the caller's array by the
+// host pool while the next chunk is in flight: a device -> host copy of doubles into a freshly allocated pageable
+// array runs at the speed of ONE driver thread that also takes the array's page faults (measured: 88 ms for
+// 1M x 50 against ~20 ms this way).  The pinned buffers live for the life of the process and are allocated with the
+// first handle (hb_create), not inside the first download.
+float* g_pinned[2] = {nullptr, nullptr};
+constexpr size_t kPinnedFloats = (size_t)8 << 20;  // 32 MiB per buffer
+bool ensure_pinned_staging() {
+  static std::mutex mk;
+  std::lock_guard<std::mutex> lk(mk);
+  if (g_pinned[0]) return true;
+  for (int i = 0; i < 2; ++i)
+    if (cudaHostAlloc((void**)&g_pinned[i], sizeof(float) * kPinnedFloats, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      if (i == 1) cudaFreeHost(g_pinned[0]);
+      g_pinned[0] = g_pinned[1] = nullptr;
+      return false;  // no pinned memory: the plain path serves
+    }
+  return true;
+}
 int download_rows_mt(hb_handle* h, const float* src, int cols, int ld, double* out, bool* done) {
-  static float* pinned[2] = {nullptr, nullptr};
-  static const size_t kFloats = (size_t)8 << 20;  // 32 MiB per buffer
+  float** pinned = g_pinned;
+  const size_t kFloats = kPinnedFloats;
   *done = false;
-  if (!pinned[0]) {
-    for (int i = 0; i < 2; ++i)
-      if (cudaHostAlloc((void**)&pinned[i], sizeof(float) * kFloats, cudaHostAllocDefault) != cudaSuccess) {
-        cudaGetLastError();
-        if (i == 1) cudaFreeHost(pinned[0]);
-        pinned[0] = pinned[1] = nullptr;
-        return 0;  // no pinned memory: the caller falls back to the plain path
-      }
-  }
+  if (!ensure_pinned_staging()) return 0;
   WidenPool* pool = widen_pool();
   const int64_t n = h->n;
   float* dev = reinterpret_cast<float*>(h->stage.p);  // two halves of the device staging buffer
@@ -1425,8 +1418,7 @@ int download_rows_mt(hb_handle* h, const float* src, int cols, int ld, double* o
   return rc;
 }
 int download_rows(hb_handle* h, const float* src, int cols, int ld, double* out) {
-  static const bool mt = getenv("HB_DOWNLOAD_MT") != nullptr;
-  if (mt) {
+  {
     bool done = false;
     TRY(download_rows_mt(h, src, cols, ld, out, &done));
     if (done) return 0;
@@ -1518,6 +1510,8 @@ int hb_create(hb_handle** out, int device) {
   cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->plan_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming);
+  ensure_pinned_staging();  // process-wide; the first handle pays for it, not the first download
+  widen_pool();
   *out = h;
   return 0;
 }
@@ -1823,7 +1817,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   // covariate tuple (2 J <= #SMs) and its ring fits shared memory; else the first persistent generation (K <= 256,
   // <= 8192 tuples, checked against the shared-memory limit); else one launch triple per block step.
   const size_t smem_limit = (size_t)227 * 1024 - 256;
-  const bool force_v1 = getenv("HB_UPDATE_V1") != nullptr, force_v2 = getenv("HB_UPDATE_V2") != nullptr;
+  const bool force_v1 = (h->kernel_set & HB_KS_UPDATE_PER_STEP) != 0, force_v2 = (h->kernel_set & HB_KS_UPDATE_TWO_PASS) != 0;
   h->coop_grid = h->num_sms;  // one persistent CTA per SM
   h->aligned_ranges = (2 * J <= h->coop_grid);
   h->u5_ring_rows = upd5_ring_rows(KS, smem_limit);
@@ -1867,12 +1861,12 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tc_len.alloc(h->tc_ntiles));
   CK(h->tc_tuple.alloc(h->tc_ntiles));
   h->use_tc_apply = (d <= 64) && (K <= 256) && apply_tc_smem_bytes((K + 7) & ~7, KS) <= 227 * 1024 &&
-                    (getenv("HB_APPLY_FFMA") == nullptr);
+                    !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
   h->use_tc_stats = (K <= 128) && (d + 1 <= 64) && stats_tc_smem_bytes(KS, h->DS) <= 227 * 1024 &&
-                    (getenv("HB_STATS_FFMA") == nullptr);
+                    !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
   h->assign_ns = assign3_smem_bytes(2, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit ? 2 : 1;
   h->use_tc_assign = (d <= 64) && (K <= 128) && assign3_smem_bytes(h->assign_ns, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit &&
-                     (getenv("HB_ASSIGN_FFMA") == nullptr);
+                     !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
   h->pt_cap = (size_t)N / TC_TM + (size_t)h->nb * J + 2;
   if (h->use_tc_assign && h->use_v4) {
     CK(h->pt_p0.alloc(2 * h->pt_cap));
@@ -1909,7 +1903,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));
     if (h->aligned_ranges) CK(h->ranges.alloc(2 * (size_t)Tplan * h->nb * h->coop_grid));
     release_peer_exchange(h);
-    if (h->use_v4 && h->world > 1 && h->world <= U4_MAXWORLD && getenv("HB_NO_PEER_EXCHANGE") == nullptr)
+    if (h->use_v4 && h->world > 1 && h->world <= U4_MAXWORLD && !(h->kernel_set & HB_KS_NO_PEER_EXCHANGE))
       TRY(setup_peer_exchange(h, Tplan));
     if (const char* e = getenv("HB_TRACE_STEPS")) {
       h->dbg_cta = atoi(e);
@@ -2306,7 +2300,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
       }
     }
   }
-  if (persistent && !update_orders && T > 0 && !h->timing && getenv("HB_NO_PLAN_OVERLAP") == nullptr) {
+  if (persistent && !update_orders && T > 0 && !h->timing && !(h->kernel_set & HB_KS_NO_PLAN_OVERLAP)) {
     // prebuild the next call's plan into the other buffer set on the side stream; it starts once this
     // call's own (main-stream) plan build and update kernel are done with the shared scan scratch
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -2473,6 +2467,7 @@ int hb_get_scalar(const hb_handle* h, int which, double* out) {
     case HB_LAMBDA_ESTIMATION: *out = h->lambda_estimation ? 1 : 0; return 0;
     case HB_WINDOW_SIZE: *out = h->window_size; return 0;
     case HB_LEGACY_CENTROID_STEP: *out = h->legacy_centroid ? 1 : 0; return 0;
+    case HB_KERNEL_SET: *out = h->kernel_set; return 0;
   }
   return 2;
 }
@@ -2488,6 +2483,7 @@ int hb_set_scalar(hb_handle* h, int which, double value) {
     case HB_EPSILON_KMEANS: h->epsilon_kmeans = (float)value; return 0;
     case HB_EPSILON_HARMONY: h->epsilon_harmony = (float)value; return 0;
     case HB_LEGACY_CENTROID_STEP: h->legacy_centroid = value != 0.0; return 0;
+    case HB_KERNEL_SET: h->kernel_set = (int)value; return 0;  // takes effect at the next hb_setup
   }
   return fail(h, 2, "scalar %d is not writable", which);
 }

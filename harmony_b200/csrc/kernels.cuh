@@ -606,40 +606,74 @@ __global__ void k_plan_segments(const int* __restrict__ Hoff, const int* __restr
     seg_start[s] = v;
   }
 }
-// Tuple-aligned work split of every block for the persistent update kernel (G CTAs): each (block, tuple)
-// segment gets a number of CTAs proportional to its length (>= 1), each CTA a contiguous slice of ONE segment.
-// One thread per (block, CTA); every thread replays the O(J) allocation (J is small in this mode: 2 J <= G).
-__global__ void k_plan_ranges(const int* __restrict__ seg_start, int nb, int J, int G, int4* __restrict__ ranges) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nb * G) return;
+// Tuple-aligned work split of every block for the persistent update kernel (G CTAs): each CTA gets a contiguous
+// slice of ONE (block, tuple) segment.  The block step ends when its most loaded CTA does, so the CTAs are dealt out
+// to minimise the largest slice: every non-empty segment starts with one CTA and the remaining ones go, one at a
+// time, to the segment with the most rows per CTA (exact comparison L_a n_b > L_b n_a; ties to the lower tuple).
+// One CTA (256 threads) per (block j = blockIdx.x, round = blockIdx.y); J <= 2 J <= G <= 1024.
+constexpr int PLAN_MAXJ = 512;
+__global__ void __launch_bounds__(256) k_plan_ranges(const int* __restrict__ seg_start, int nb, int J, int G,
+                                                     int4* __restrict__ ranges) {
+  __shared__ int L[PLAN_MAXJ], nq[PLAN_MAXJ], first[PLAN_MAXJ + 1];
   seg_start += (size_t)blockIdx.y * ((size_t)nb * J + 1);  // blockIdx.y: round of the batch
   ranges += (size_t)blockIdx.y * (size_t)nb * G;
-  const int j = idx / G, me_cta = idx - j * G;
+  const int j = blockIdx.x;
   const int* segs = seg_start + (size_t)j * J;
-  const int b0 = segs[0];
-  const long long blen = segs[J] - b0;
-  int4 out = make_int4(b0, b0, 0, 0);
-  if (blen > 0) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int q = tid; q < J; q += blockDim.x) {
+    L[q] = segs[q + 1] - segs[q];
+    nq[q] = L[q] > 0 ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid < 32) {
     int nonempty = 0;
-    for (int q = 0; q < J; ++q) nonempty += (segs[q + 1] > segs[q]);
-    int start = 0;
-    for (int q = 0; q < J; ++q) {
-      const int L = segs[q + 1] - segs[q];
-      if (L == 0) continue;
-      --nonempty;
-      int end = (int)(((long long)G * (segs[q + 1] - b0)) / blen);
-      if (end < start + 1) end = start + 1;
-      if (end > G - nonempty) end = G - nonempty;
-      if (nonempty == 0) end = G;
-      if (me_cta >= start && me_cta < end) {
-        const int nq = end - start, me = me_cta - start;
-        out = make_int4(segs[q] + (int)(((long long)L * me) / nq), segs[q] + (int)(((long long)L * (me + 1)) / nq), q, 0);
-        break;
+    for (int q = lane; q < J; q += 32) nonempty += nq[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nonempty += __shfl_xor_sync(0xffffffffu, nonempty, o);
+    for (int rem = (nonempty > 0) ? G - nonempty : 0; rem > 0; --rem) {
+      long long bl = 0, bn = 1;  // best ratio bl / bn of this lane
+      int bq = J;
+      for (int q = lane; q < J; q += 32)
+        if (nq[q] > 0 && (long long)L[q] * bn > bl * (long long)nq[q]) {
+          bl = L[q];
+          bn = nq[q];
+          bq = q;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long ol = __shfl_xor_sync(0xffffffffu, bl, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+        const int oq = __shfl_xor_sync(0xffffffffu, bq, o);
+        const long long lhs = ol * bn, rhs = bl * on;
+        if (lhs > rhs || (lhs == rhs && oq < bq)) {
+          bl = ol;
+          bn = on;
+          bq = oq;
+        }
       }
-      start = end;
+      if (lane == 0 && bq < J) nq[bq]++;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      int c = 0;
+      for (int q = 0; q < J; ++q) {
+        first[q] = c;
+        c += nq[q];
+      }
+      first[J] = c;
     }
   }
-  ranges[idx] = out;
+  __syncthreads();
+  const int b0 = segs[0];
+  for (int c = tid; c < G; c += blockDim.x) {
+    int4 out = make_int4(b0, b0, 0, 0);
+    if (c < first[J]) {
+      int q = 0;
+      while (first[q + 1] <= c) ++q;  // J is small
+      const int n = nq[q], me = c - first[q];
+      out = make_int4(segs[q] + (int)(((long long)L[q] * me) / n), segs[q] + (int)(((long long)L[q] * (me + 1)) / n), q, 0);
+    }
+    ranges[(size_t)j * G + c] = out;
+  }
 }
 // 128-row tiles of the (block, tuple) segments of a round (the assignment step in plan order)
 __global__ void k_plan_tilecount128(const int* __restrict__ seg_start, int S, int* __restrict__ tile_base) {

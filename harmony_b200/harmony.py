@@ -18,10 +18,10 @@ FIELD = {"Z_corr": 0, "Z_orig": 1, "R": 2, "Y": 3, "O": 4, "E": 5, "W": 6, "Pr_b
          "lambda_mat": 10, "lambda": 11}
 SCALAR = {"N": 0, "B": 1, "K": 2, "d": 3, "C": 4, "alpha": 5, "max_iter_kmeans": 6, "block_size": 7,
           "epsilon_kmeans": 8, "epsilon_harmony": 9, "N_local": 10, "lambda_estimation": 11, "window_size": 12,
-          "legacy_centroid_step": 13}
+          "legacy_centroid_step": 13, "kernel_set": 14}
 TRACE = {"objective_kmeans": 0, "objective_kmeans_dist": 1, "objective_kmeans_entropy": 2,
          "objective_kmeans_cross": 3, "objective_harmony": 4, "kmeans_rounds": 5}
-_INT_SCALARS = ("N", "B", "K", "d", "C", "max_iter_kmeans", "N_local", "window_size", "legacy_centroid_step")
+_INT_SCALARS = ("N", "B", "K", "d", "C", "max_iter_kmeans", "N_local", "window_size", "legacy_centroid_step", "kernel_set")
 
 
 def _ptr(a):
@@ -140,6 +140,19 @@ class harmony:
             raise ValueError("Y0 must be d x K")
         self._check(self._L.hb_init_cluster(self._h, _ptr(Y0)))
 
+    def set_abort_callback(self, fn):
+        """Progress::check_abort of the reference (harmony.cpp:233, 355): ``fn()`` is polled before the clustering
+        rounds of every cluster_cpp call (and between them); a true value makes cluster_cpp return -1, which
+        harmonize() turns into "terminated by user" (R/utils.R:27-29).  ``None`` removes the callback."""
+        import ctypes
+        if fn is None:
+            self._abort_cb = None
+            self._check(self._L.hb_set_abort_callback(self._h, None, None))
+            return
+        proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
+        self._abort_cb = proto(lambda _user: 1 if fn() else 0)   # keep the trampoline alive with the object
+        self._check(self._L.hb_set_abort_callback(self._h, ctypes.cast(self._abort_cb, ctypes.c_void_p), None))
+
     def cluster_cpp(self, update_orders=None):
         """harmony::cluster_cpp -> 0 / -1 (aborted).  ``update_orders``: [max_iter_kmeans, N] int64,
         row t = the shuffled update order of the t-th update_R call (harmony.cpp:272-273)."""
@@ -187,7 +200,7 @@ class harmony:
     def __getattr__(self, name):
         if name.startswith("_"):
             raise AttributeError(name)
-        if name in ("N", "B", "K", "d", "alpha", "max_iter_kmeans", "legacy_centroid_step"):
+        if name in ("N", "B", "K", "d", "alpha", "max_iter_kmeans", "legacy_centroid_step", "kernel_set"):
             return self._scalar(name)
         if name == "R":
             return self.getR()
@@ -220,7 +233,7 @@ class harmony:
         if name.startswith("_"):
             object.__setattr__(self, name, value)
             return
-        if name in ("alpha", "max_iter_kmeans", "legacy_centroid_step"):
+        if name in ("alpha", "max_iter_kmeans", "legacy_centroid_step", "kernel_set"):
             self._check(self._L.hb_set_scalar(self._h, SCALAR[name], float(value)))
             return
         shapes = {"Y": ("Y", "d", "K"), "R": ("R", "K", "N_local"), "O": ("O", "K", "B"), "E": ("E", "K", "B")}

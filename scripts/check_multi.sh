@@ -8,12 +8,11 @@ mkdir -p gpurun_out
 nvidia-smi -L
 timeout 600 python -m pytest tests/test_gpu_multi.py -x -q -m gpu -s 2>&1 | tail -15 | tee gpurun_out/multi_parity_${N}gpu.log
 for mode in xch nccl; do
-  if [ $mode = nccl ]; then export HB_NO_PEER_EXCHANGE=1; else unset HB_NO_PEER_EXCHANGE; fi
+  if [ $mode = nccl ]; then KS="--kernel-set 8"; else KS=""; fi
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
-    bench.py --gpus $N --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_${N}gpu_${mode}.json 2> gpurun_out/bench_${N}gpu_${mode}.err
+    bench.py --gpus $N --steps 10 --warmup 3 --no-e2e --no-cpu-baseline $KS > gpurun_out/bench_${N}gpu_${mode}.json 2> gpurun_out/bench_${N}gpu_${mode}.err
   tail -3 gpurun_out/bench_${N}gpu_${mode}.err
 done
-unset HB_NO_PEER_EXCHANGE
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_1gpu_ref.json
 python - <<PY
 import json

@@ -32,9 +32,11 @@ ARGMAX_GAP_MAX = 1e-3     # a differing hard index is only tolerated on cells th
 ARGMAX_FRAC_MAX = 5e-4    # ... and on at most this fraction of the cells
 
 
-def run_gpu(a, Y0, n_iter, perms):
+def run_gpu(a, Y0, n_iter, perms, kernel_set=0):
     from harmony_b200.harmony import harmony
     g = harmony()
+    if kernel_set:
+        g.kernel_set = kernel_set   # test hook: force the kernels that serve out-of-limit shapes (read by setup)
     g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], a["max_iter_kmeans"],
             a["epsilon_kmeans"], a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"],
             a["batch_proportion_cutoff"], False)
@@ -317,16 +319,16 @@ def test_field_writes_and_resume():
     assert len(g.objective_harmony) == 3
 
 
-@pytest.mark.parametrize("env", [
-    {"HB_ASSIGN_FFMA": "1", "HB_STATS_FFMA": "1", "HB_APPLY_FFMA": "1"},   # fp32 FFMA kernels instead of tcgen05
-    {"HB_UPDATE_V1": "1"},                                                 # three launches per block step
-    {"HB_NO_PLAN_OVERLAP": "1"},
+@pytest.mark.parametrize("kernel_set", [
+    1,    # HB_KS_FFMA_CONTRACTIONS: fp32 FFMA assignment / statistics / apply instead of tcgen05
+    2,    # HB_KS_UPDATE_PER_STEP: three launches per block step
+    4,    # HB_KS_UPDATE_TWO_PASS: first persistent update_R generation
+    16,   # HB_KS_NO_PLAN_OVERLAP
 ])
-def test_fallback_kernels_match_oracle(env, monkeypatch):
-    """The FFMA / per-step kernels that serve shapes outside the tensor-core kernels' limits
-    (d > 64, K > 128, > 8192 tuples) are the in-repo correctness anchors: same parity bar."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+def test_fallback_kernels_match_oracle(kernel_set):
+    """The FFMA / per-step / two-pass kernels that serve shapes outside the default kernels' limits (d > 64, K > 128,
+    too many tuples for tuple-aligned CTA slices) are forced onto a shape the default kernels would take through the
+    HB_KERNEL_SET test hook of the handle (include/harmony_b200.h) and held to the same parity bar."""
     (Z, meta), vars_use, kw = CASES["synthetic_3cov_nested"]()
     a = prepare_inputs(Z, meta, vars_use, early_stop=False, **kw)
     N, T = Z.shape[0], a["max_iter_kmeans"]
@@ -334,5 +336,5 @@ def test_fallback_kernels_match_oracle(env, monkeypatch):
     perms = make_perms(N, 2 * T, 23).reshape(2, T, N)
     o32, _, _ = run_oracle(a, Y0, 2, perms=perms)
     o64, _, _ = run_oracle(a, Y0, 2, perms=perms, double=True)
-    g, iters = run_gpu(a, Y0, 2, perms)
-    compare(g, o32, o64, "fallback " + "+".join(env))
+    g, iters = run_gpu(a, Y0, 2, perms, kernel_set=kernel_set)
+    compare(g, o32, o64, f"kernel_set {kernel_set}")

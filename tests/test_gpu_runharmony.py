@@ -113,7 +113,7 @@ def test_properties_at_full_size():
             np.array([20], dtype=np.int32), 1e-5)
     g.set_seed(7)
     g.init_cluster_cpp()
-    N_b = np.bincount(b, minlength=20)
+    N_b = np.bincount(b[:, 0], minlength=20)
     for it in range(2):
         assert g.cluster_cpp() == 0
         O, E = g.O, g.E
@@ -221,3 +221,28 @@ def test_native_kmeans_centers_follows_the_reference_rule():
     if np.array_equal(cells, cells_n):
         Yn = Yn / np.linalg.norm(Yn, axis=1, keepdims=True)
         np.testing.assert_allclose(g.Y.T, Yn, atol=2e-3)       # Lloyd in fp32 with atomics vs fp64: boundary cells may flip
+
+
+def test_abort_callback_stops_cluster_cpp():
+    """hb_set_abort_callback = Progress::check_abort (harmony.cpp:233): cluster_cpp returns -1 once the callback
+    says so, harmonize() reports "terminated by user" like R/utils.R:27-29, and the object stays usable."""
+    from harmony_b200 import prepare_inputs
+    from harmony_b200.harmony import harmony
+    from harmony_b200.utils import harmonize
+    from helpers import make_Y0
+    Z, meta = load_cell_lines(True)
+    a = prepare_inputs(Z, meta, "dataset", nclust=5, early_stop=False)
+    g = harmony(device=0)
+    g.setup(a["Z"], a["phi_i"], a["sigma"], a["theta"], a["lambda_"], a["alpha"], a["max_iter_kmeans"],
+            a["epsilon_kmeans"], a["epsilon_harmony"], a["K"], a["block_size"], a["B_vec"], a["batch_proportion_cutoff"])
+    g.init_cluster_cpp(make_Y0(Z, a["K"], 0))
+    calls, state = [], {"abort": False}
+    g.set_abort_callback(lambda: calls.append(1) or state["abort"])
+    assert g.cluster_cpp() == 0            # polled, not yet aborting
+    g.moe_correct_ridge_cpp()
+    assert len(calls) >= 1
+    state["abort"] = True
+    with pytest.raises(KeyboardInterrupt):
+        harmonize(g, 5, verbose=False)
+    g.set_abort_callback(None)
+    assert g.cluster_cpp() == 0            # the handle survives an abort
