@@ -13,8 +13,10 @@
 //   * A = V_q^T is rebuilt by the same threads when the tuple changes (after the previous tile's MMAs);
 //   * epilogue as before: TMEM lane = embedding column c, Zc[cell][c] = Zo[cell][c] - D'[c][cell], coalesced
 //     across the warp; one warp pair per accumulator, tile records fetched one tile ahead.
-// Warp roles (448 threads): 0 MMA issuer, 2-5 loaders / converters, 8-9 and 12-13 epilogue (TMEM lane quarters
-// 0 and 1 of accumulator 0 / 1), the others idle.  Limits: d <= 64, K <= 256 (shared memory).
+// Warp roles (448 threads): 0 MMA issuer, 2-5 loaders / converters, 6-9 / 10-13 epilogue of accumulator 0 / 1 (a warp
+// serves TMEM lane quarter warp % 4 = 32 embedding columns; quarters beyond d idle).  Limits per launch: d <= 128 and
+// <= 112 clusters (shared memory); more clusters run as several launches over cluster ranges, each subtracting its
+// share from the partial result (the first from Zo).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -24,6 +26,7 @@ namespace hb {
 constexpr int AP_TN = 64;         // cells per tile (= UMMA N), equals the static tile size TM
 constexpr int AP_THREADS = 448;   // 14 warps
 constexpr int AP_LOAD = 128;      // loader / converter threads (warps 2-5)
+constexpr int AP_MAXK = 112;      // clusters per launch: (2 x 128 + 4 x 64) x KD floats of operands must fit 227 KB
 
 struct ApplyTcArgs {
   const float* R;   // [n][KS]
@@ -33,42 +36,56 @@ struct ApplyTcArgs {
   const int* tile_cell0;
   const int* tile_len;
   const int* tile_tuple;
-  int ntiles, d, K, KS, DS, KD;  // KD = K rounded up to a multiple of 8
+  int ntiles, d, K, KS, DS;
+  int k_off, Kp, KD;  // this launch: clusters [k_off, k_off + Kp) (k_off a multiple of 4), KD = Kp rounded up to 8
+  const float* minuend;  // Zo for the first cluster range, Zc (the partial result) for the following ones
   int tiles_per_cta;
   long long* dbg;
 };
 
-__host__ __device__ inline size_t apply_tc_smem_bytes(int KD, int KS) {
-  // A hi/lo: 2 x 128 x KD; B hi/lo, two stages: 2 x 2 x 64 x KD
-  (void)KS;
-  return sizeof(float) * (2 * (size_t)128 * KD + 4 * (size_t)AP_TN * KD) + 1024;
+// A = V_q^T is stored with AROWS = 64 rows per 16-byte K chunk when d <= 64 (descriptor LBO = 64 x 16 bytes): the MMA
+// still reads M = 128 rows, rows 64-127 alias the next chunk and land in accumulator lanes nobody reads.  The freed
+// 53 KB buy a third operand stage.
+__host__ __device__ inline int apply_tc_arows(int d) { return d <= 64 ? 64 : 128; }
+__host__ __device__ inline size_t apply_tc_smem_bytes_n(int KD, int d, int nst) {
+  // A hi/lo: 2 x AROWS x KD (+ one chunk plane of slack for the aliased rows of the last chunk); B hi/lo: nst x 2 x 64 x KD
+  return sizeof(float) * (2 * (size_t)apply_tc_arows(d) * KD + 2 * (size_t)nst * AP_TN * KD) + 1024;
 }
+__host__ __device__ inline int apply_tc_stages(int KD, int d) {
+  return apply_tc_smem_bytes_n(KD, d, 3) <= (size_t)227 * 1024 - 256 ? 3 : 2;
+}
+__host__ __device__ inline size_t apply_tc_smem_bytes(int KD, int d) { return apply_tc_smem_bytes_n(KD, d, apply_tc_stages(KD, d)); }
 
 __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int KD = a.KD, K = a.K, d = a.d, KS = a.KS, DS = a.DS;
-  float* Ahi = reinterpret_cast<float*>(smem_raw);  // [KD/4][128][4]   V_q^T
-  float* Alo = Ahi + (size_t)128 * KD;
-  float* Bhi = Alo + (size_t)128 * KD;               // [2][KD/4][64][4]  raw R rows = hi operand
-  float* Blo = Bhi + 2 * (size_t)AP_TN * KD;         // [2][KD/4][64][4]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Blo + 2 * (size_t)AP_TN * KD);
-  uint64_t* lo_full = bars + 0;    // [2]  loaders (128): operands of the stage complete
-  uint64_t* st_empty = bars + 2;   // [2]  tcgen05.commit: operands consumed
-  uint64_t* t_full = bars + 4;     // [2]  tcgen05.commit: accumulator ready
-  uint64_t* t_empty = bars + 6;    // [2]  epilogue pair (64): accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int KD = a.KD, K = a.K, d = a.d, KS = a.KS, DS = a.DS, Kp = a.Kp;
+  const int nq = (d + 31) >> 5;  // TMEM lane quarters in use (embedding columns / 32)
+  const int AR = apply_tc_arows(d);       // rows of A per K chunk
+  const int NST = apply_tc_stages(KD, d);  // operand stages of B
+  const int BST = AP_TN * KD;              // floats per B tile
+  float* Ahi = reinterpret_cast<float*>(smem_raw);  // [KD/4][AR][4]   V_q^T
+  float* Alo = Ahi + (size_t)AR * KD;
+  float* Bhi = Alo + (size_t)AR * KD;                // [NST][KD/4][64][4]  raw R rows = hi operand
+  float* Blo = Bhi + (size_t)NST * BST;              // [NST][KD/4][64][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Blo + (size_t)NST * BST);
+  uint64_t* lo_full = bars + 0;    // [3]  loaders (128): operands of the stage complete
+  uint64_t* st_empty = bars + 3;   // [3]  tcgen05.commit: operands consumed
+  uint64_t* t_full = bars + 6;     // [2]  tcgen05.commit: accumulator ready
+  uint64_t* t_empty = bars + 8;    // [2]  epilogue warps (32 per lane quarter in use): accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nch = KD >> 2;   // 16-byte chunks along K in the operand tiles
-  const int KS4 = KS >> 2;   // ... in a row of R
+  const int R4 = ((KS - a.k_off < KD ? KS - a.k_off : KD)) >> 2;   // 16-byte chunks of this launch's cluster range in a row of R
 
   // the padding chunks of B (k >= KS) are never written by the loaders and must be zero (0 x NaN would poison D')
-  for (int i = tid; i < 4 * AP_TN * KD; i += AP_THREADS) Bhi[i] = 0.f;
+  for (int i = tid; i < 2 * NST * BST; i += AP_THREADS) Bhi[i] = 0.f;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       umma::mbar_init(lo_full + i, AP_LOAD);
       umma::mbar_init(st_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       umma::mbar_init(t_full + i, 1);
-      umma::mbar_init(t_empty + i, 64);
+      umma::mbar_init(t_empty + i, 32 * nq);
     }
     umma::fence_barrier_init();
   }
@@ -93,18 +110,18 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
     // =============================== MMA issuer (one thread) ===============================
     if (lane == 0) {
       const uint32_t idesc = umma::make_idesc_tf32(128, AP_TN, 0, 0);
-      const uint32_t lboA = 128 * 16, lboB = AP_TN * 16, sbo = 128;
+      const uint32_t lboA = (uint32_t)AR * 16, lboB = AP_TN * 16, sbo = 128;
       const uint32_t aH = umma::smem_u32(Ahi), aL = umma::smem_u32(Alo);
       int it = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const int s = it & 1, use = it >> 1;
-        umma::mbar_wait(lo_full + s, use & 1);
+        const int s = it % NST, acc = it & 1;
+        umma::mbar_wait(lo_full + s, (it / NST) & 1);
         stamp(it, 5);
-        if (use >= 1) umma::mbar_wait(t_empty + s, (use - 1) & 1);
+        if (it >= 2) umma::mbar_wait(t_empty + acc, ((it >> 1) - 1) & 1);
         stamp(it, 6);
         umma::fence_after_sync();
-        const uint32_t bH = umma::smem_u32(Bhi + (size_t)s * AP_TN * KD), bL = umma::smem_u32(Blo + (size_t)s * AP_TN * KD);
-        const uint32_t dt = tmem + s * AP_TN;
+        const uint32_t bH = umma::smem_u32(Bhi + (size_t)s * BST), bL = umma::smem_u32(Blo + (size_t)s * BST);
+        const uint32_t dt = tmem + acc * AP_TN;
         uint32_t accum = 0;
         for (int ks = 0; ks < KD / 8; ++ks) {
           const uint64_t ah = umma::make_desc(aH + ks * 2 * lboA, lboA, sbo);
@@ -117,7 +134,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
           accum = 1;
         }
         umma::mma_commit(st_empty + s);
-        umma::mma_commit(t_full + s);
+        umma::mma_commit(t_full + acc);
         stamp(it, 7);
       }
     }
@@ -126,8 +143,8 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
     const int lt = tid - 64;             // 0..127
     const int cell = lt & (AP_TN - 1);   // row of the tile
     const int half = lt >> 6;            // which half of the row's 16-byte pieces
-    const int hsplit = (KS4 + 1) >> 1;
-    const int c_lo = half ? hsplit : 0, c_hi = half ? KS4 : hsplit;
+    const int hsplit = (R4 + 1) >> 1;
+    const int c_lo = half ? hsplit : 0, c_hi = half ? R4 : hsplit;
     auto meta = [&](int it, int& cell0, int& len, int& q) {
       const int tile = t_begin + it;
       cell0 = 0;
@@ -139,87 +156,84 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
         q = __ldg(a.tile_tuple + tile);
       }
     };
-    auto issue_row = [&](int it, int cell0, int len) {  // tile `it` -> stage it & 1; always commits
+    auto issue_row = [&](int it, int cell0, int len) {  // tile `it` -> stage it % NST; always commits
       if (cell < len) {
-        const float* src = a.R + (size_t)(cell0 + cell) * KS;
-        const unsigned dst = umma::smem_u32(Bhi + (size_t)(it & 1) * AP_TN * KD + (size_t)cell * 4);
+        const float* src = a.R + (size_t)(cell0 + cell) * KS + a.k_off;
+        const unsigned dst = umma::smem_u32(Bhi + (size_t)(it % NST) * BST + (size_t)cell * 4);
         for (int c = c_lo; c < c_hi; ++c)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)c * (AP_TN * 16u)), "l"(src + 4 * c) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    int c0_0, len0, q0, c0_1, len1, q1, c0_2, len2, q2;
-    meta(0, c0_0, len0, q0);
-    meta(1, c0_1, len1, q1);
-    meta(2, c0_2, len2, q2);
-    issue_row(0, c0_0, len0);
+    // tile records run NST tiles ahead of the conversion: m[j] = record of tile it + j
+    int mc[4], ml[4], mq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) meta(j, mc[j], ml[j], mq[j]);
+    issue_row(0, mc[0], ml[0]);  // prologue: NST - 1 tiles in flight
+    if (NST == 3) issue_row(1, mc[1], ml[1]);
     int cur_q = -1;
     int it = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-      const int s = it & 1;
+      const int s = it % NST;
       if (lt == 0) stamp(it, 0);
-      bool prev_done = (it == 0);  // the MMAs of tile it - 1 are known to be complete
-      if (tile + 1 < t_end) {
-        if (it >= 1) {
-          umma::mbar_wait(st_empty + ((it + 1) & 1), ((it - 1) >> 1) & 1);  // MMAs of tile it - 1: its stage is free
-          prev_done = true;
-        }
-        if (lt == 0) stamp(it, 1);
-        issue_row(it + 1, c0_1, len1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
+      if (NST == 3)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's pieces have landed (tile it + 1 may be in flight)
+      else
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      if (lt == 0) stamp(it, 2);
-      if (q0 != cur_q) {
+      if (lt == 0) stamp(it, 1);
+      if (mq[0] != cur_q) {
         // new tuple: A = V_q^T (k contiguous per embedding column c), tf32 hi/lo — after the previous tile's MMAs
-        if (!prev_done) umma::mbar_wait(st_empty + ((it + 1) & 1), ((it - 1) >> 1) & 1);
-        const float* Vq = a.V + (size_t)q0 * K * d;
-        for (int idx = lt; idx < 128 * KD; idx += AP_LOAD) {
-          const int k = idx / 128, c = idx - k * 128;
-          const float v = (k < K && c < d) ? Vq[(size_t)k * d + c] : 0.f;
+        if (it >= 1) umma::mbar_wait(st_empty + ((it - 1) % NST), ((it - 1) / NST) & 1);
+        const float* Vq = a.V + ((size_t)mq[0] * K + a.k_off) * d;
+        for (int idx = lt; idx < AR * KD; idx += AP_LOAD) {
+          const int k = idx / AR, c = idx - k * AR;
+          const float v = (k < Kp && c < d) ? Vq[(size_t)k * d + c] : 0.f;
           float hi, lo;
           umma::split_tf32(v, hi, lo);
-          const int off = ((k >> 2) * 128 + c) * 4 + (k & 3);
+          const int off = ((k >> 2) * AR + c) * 4 + (k & 3);
           Ahi[off] = hi;
           Alo[off] = lo;
         }
-        cur_q = q0;
+        cur_q = mq[0];
       }
-      // `lo` pieces of this thread's half row (rows beyond the tile keep whatever the stage holds: their columns of D'
-      // are not read)
+      // `lo` pieces of this thread's half row: the remainder z - trunc_tf32(z) is exact in fp32; the tensor core
+      // truncates it to tf32 like it truncates z itself (relative error of the pair <= 2^-20).  Rows beyond the
+      // tile keep whatever the stage holds: their columns of D' are not read.
       {
-        const float* hi = Bhi + (size_t)s * AP_TN * KD + (size_t)cell * 4;
-        float* lo = Blo + (size_t)s * AP_TN * KD + (size_t)cell * 4;
-        if (cell < len0) {
+        const float* hi = Bhi + (size_t)s * BST + (size_t)cell * 4;
+        float* lo = Blo + (size_t)s * BST + (size_t)cell * 4;
+        if (cell < ml[0]) {
           for (int c = c_lo; c < c_hi; ++c) {
             const float4 z = *reinterpret_cast<const float4*>(hi + (size_t)c * AP_TN * 4);
             float4 l4;
-            // the tensor core reads trunc_tf32(z); the remainder is exact in fp32 and is rounded to tf32 here
-            l4.x = umma::round_tf32(z.x - __uint_as_float(__float_as_uint(z.x) & 0xffffe000u));
-            l4.y = umma::round_tf32(z.y - __uint_as_float(__float_as_uint(z.y) & 0xffffe000u));
-            l4.z = umma::round_tf32(z.z - __uint_as_float(__float_as_uint(z.z) & 0xffffe000u));
-            l4.w = umma::round_tf32(z.w - __uint_as_float(__float_as_uint(z.w) & 0xffffe000u));
+            l4.x = z.x - __uint_as_float(__float_as_uint(z.x) & 0xffffe000u);
+            l4.y = z.y - __uint_as_float(__float_as_uint(z.y) & 0xffffe000u);
+            l4.z = z.z - __uint_as_float(__float_as_uint(z.z) & 0xffffe000u);
+            l4.w = z.w - __uint_as_float(__float_as_uint(z.w) & 0xffffe000u);
             *reinterpret_cast<float4*>(lo + (size_t)c * AP_TN * 4) = l4;
           }
         }
       }
       umma::fence_proxy_async();  // this thread's cp.async pieces (observed above), `lo` and A writes -> tensor core
       umma::mbar_arrive(lo_full + s);
+      if (lt == 0) stamp(it, 2);
+      // tile it + NST - 1 goes into the stage tile it - 1 used: after that tile's MMAs
+      if (tile + NST - 1 < t_end && it >= 1) umma::mbar_wait(st_empty + ((it - 1) % NST), ((it - 1) / NST) & 1);
+      issue_row(it + NST - 1, NST == 3 ? mc[2] : mc[1], NST == 3 ? ml[2] : ml[1]);
       if (lt == 0) stamp(it, 3);
-      c0_0 = c0_1;
-      len0 = len1;
-      q0 = q1;
-      c0_1 = c0_2;
-      len1 = len2;
-      q1 = q2;
-      meta(it + 3, c0_2, len2, q2);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        mc[j] = mc[j + 1];
+        ml[j] = ml[j + 1];
+        mq[j] = mq[j + 1];
+      }
+      meta(it + 4, mc[3], ml[3], mq[3]);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == 8 || warp == 9 || warp == 12 || warp == 13) {
-    // =============================== epilogue (one warp pair per accumulator) ===============================
-    const int es = (warp >= 12) ? 1 : 0;     // accumulator served by this pair
-    const int wq = warp & 3;                 // TMEM lane quarter: 0 or 1
+  } else if (warp >= 6 && (warp & 3) < nq) {
+    // =============================== epilogue (warps 6-9: accumulator 0, 10-13: accumulator 1) ===============================
+    const int es = (warp >= 10) ? 1 : 0;     // accumulator served by this warp
+    const int wq = warp & 3;                 // TMEM lane quarter (hardware: warp % 4)
     const int c = wq * 32 + lane;            // embedding column = TMEM lane
     int use = 0;
     int cell0_n = 0, len_n = 0;
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
       float zo[AP_TN];
       if (c < d) {
 #pragma unroll
-        for (int j = 0; j < AP_TN; ++j) zo[j] = (j < len) ? ld_stream(a.Zo + (size_t)(cell0 + j) * DS + c) : 0.f;
+        for (int j = 0; j < AP_TN; ++j) zo[j] = (j < len) ? ld_stream(a.minuend + (size_t)(cell0 + j) * DS + c) : 0.f;
       }
       umma::mbar_wait(t_full + es, use & 1);
       umma::fence_after_sync();

@@ -213,24 +213,47 @@ struct XchArea {
   bool leased = false;
 };
 
+// Device buffers come from the device's default memory pool (stream-ordered allocator), whose release threshold
+// hb_create raises to "keep everything": a model created after another one was dropped reuses the cached memory
+// instead of paying cudaMalloc's OS mapping again (measured: 44 ms of a 100 ms end-to-end run at 1M cells).
+// Frees keep cudaFree's contract: nothing of the device may still be using the memory.
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaDeviceSynchronize();
+      if (cudaFreeAsync(p, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+      }
+    }
     p = nullptr;
     n = 0;
   }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);  // ordered on the (idle) default stream: usable from any stream now
+    if (e != cudaSuccess) {  // no pool support / pool exhausted: plain allocation
+      cudaGetLastError();
+      e = cudaMalloc((void**)&p, count * sizeof(T));
+    }
     if (e == cudaSuccess) n = count;
     return e;
   }
 };
+void keep_pool_memory(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+}
 
 }  // namespace
 
@@ -1208,8 +1231,12 @@ int run_correct(hb_handle* h) {
       const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
       const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
       CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-      k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
-      CKL();
+      // one launch per 128 clusters x 64 columns of [Zo | 1] (K = 100, d = 50: one launch)
+      for (t.k_off = 0; t.k_off < K; t.k_off += 128)
+        for (t.c_off = 0; t.c_off < D1; t.c_off += 64) {
+          k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+          CKL();
+        }
     } else {
     StatsArgs a;
       a.R = h->R.p;
@@ -1279,7 +1306,6 @@ int run_correct(hb_handle* h) {
     a.K = K;
     a.KS = h->KS;
     a.DS = h->DS;
-    a.KD = (K + 7) & ~7;
     a.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
     a.dbg = nullptr;
     static int ap_calls = 0;
@@ -1291,11 +1317,22 @@ int run_correct(hb_handle* h) {
     }
     const int grid = (h->ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
     {
-      const size_t smem = apply_tc_smem_bytes(a.KD, h->KS);
-      CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
+      // cluster ranges of at most AP_MAXK clusters (shared memory), equal sizes, multiples of 8: the first launch
+      // subtracts its share from Zo, the following ones from the partial result in Zc
+      const int npass = (K + AP_MAXK - 1) / AP_MAXK;
+      const int Kpass = (((K + npass - 1) / npass) + 7) & ~7;
+      for (int k_off = 0; k_off < K; k_off += Kpass) {
+        a.k_off = k_off;
+        a.Kp = std::min(Kpass, K - k_off);
+        a.KD = (a.Kp + 7) & ~7;
+        a.minuend = (k_off == 0) ? h->Zo.p : h->Zc.p;
+        const size_t smem = apply_tc_smem_bytes(a.KD, d);
+        CK(cudaFuncSetAttribute(k_apply_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_apply_tc<<<grid, AP_THREADS, smem, h->stream>>>(a);
+        CKL();
+        a.dbg = nullptr;
+      }
     }
-    CKL();
     if (tracing) {
       std::vector<long long> st(32 * 16);
       CK(cudaMemcpyAsync(st.data(), h->dbg.p, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -1511,6 +1548,7 @@ int hb_create(hb_handle** out, int device) {
   cudaEventCreateWithFlags(&h->plan_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev0, cudaEventDisableTiming);
   ensure_pinned_staging();  // process-wide; the first handle pays for it, not the first download
+  keep_pool_memory(device);
   widen_pool();
   *out = h;
   return 0;
@@ -1860,10 +1898,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   CK(h->tc_cell0.alloc(h->tc_ntiles));
   CK(h->tc_len.alloc(h->tc_ntiles));
   CK(h->tc_tuple.alloc(h->tc_ntiles));
-  h->use_tc_apply = (d <= 64) && (K <= 256) && apply_tc_smem_bytes((K + 7) & ~7, KS) <= 227 * 1024 &&
-                    !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
-  h->use_tc_stats = (K <= 128) && (d + 1 <= 64) && stats_tc_smem_bytes(KS, h->DS) <= 227 * 1024 &&
-                    !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
+  h->use_tc_apply = (d <= 128) && !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);   // cluster ranges of <= AP_MAXK per launch
+  h->use_tc_stats = !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);                  // 128 clusters x 64 columns per launch
   h->assign_ns = assign3_smem_bytes(2, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit ? 2 : 1;
   h->use_tc_assign = (d <= 64) && (K <= 128) && assign3_smem_bytes(h->assign_ns, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit &&
                      !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
@@ -2119,8 +2155,11 @@ int legacy_centroid_step(hb_handle* h) {
     const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
     const size_t smem_tc = stats_tc_smem_bytes(KS, h->DS);
     CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-    k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
-    CKL();
+    for (t.k_off = 0; t.k_off < K; t.k_off += 128)
+      for (t.c_off = 0; t.c_off < D1; t.c_off += 64) {
+        k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+        CKL();
+      }
   } else {
     StatsArgs a;
     a.R = h->R.p;

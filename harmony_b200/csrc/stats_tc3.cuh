@@ -31,6 +31,7 @@ struct StatsTcArgs {
   const int* tile_tuple;
   float* S;         // [J][K][d+1]
   int ntiles, d, K, KS, DS, tiles_per_cta;
+  int k_off, c_off;  // this launch: clusters [k_off, k_off + 128) x columns [c_off, c_off + 64) of [Zo | 1] (wider shapes: several launches)
 };
 
 __host__ __device__ inline size_t stats_tc_smem_bytes(int KS, int DS) {
@@ -122,14 +123,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
         cell0 = __ldg(a.tile_cell0 + tile);
         len = __ldg(a.tile_len + tile);
       }
-      const float* rR = a.R + (size_t)cell0 * KS + kA;
-      const float* rZ = a.Zo + (size_t)cell0 * DS + cB;
+      const float* rR = a.R + (size_t)cell0 * KS + a.k_off + kA;
+      const float* rZ = a.Zo + (size_t)cell0 * DS + a.c_off + cB;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int cell = 4 * (ccA + 2 * i) + j;
-          vA[i][j] = (cell < len && kA < K) ? ld_stream(rR + (size_t)cell * KS) : 0.f;
+          vA[i][j] = (cell < len && a.k_off + kA < K) ? ld_stream(rR + (size_t)cell * KS) : 0.f;
         }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
         for (int j = 0; j < 4; ++j) {
           const int cell = 4 * (ccB + 4 * i) + j;
           float v = 0.f;
-          if (cell < len) v = (cB < d) ? ld_stream(rZ + (size_t)cell * DS) : (cB == d ? 1.f : 0.f);  // column d: the ones column
+          if (cell < len) v = (a.c_off + cB < d) ? ld_stream(rZ + (size_t)cell * DS) : (a.c_off + cB == d ? 1.f : 0.f);  // column d: the ones column
           vB[i][j] = v;
         }
     };
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
         // flush the accumulator of this tuple: thread = cluster row (TMEM lane), 64 columns
         umma::mbar_wait(acc_full, runs & 1);
         umma::fence_after_sync();
-        const int wq = warp & 3, k = wq * 32 + lane;
+        const int wq = warp & 3, k = a.k_off + wq * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         for (int c0 = 0; c0 < 64; c0 += 16) {
           float v[16];
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
           if (k < K) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (c0 + i < D1) atomicAdd(a.S + ((size_t)q * K + k) * D1 + c0 + i, v[i]);
+              if (a.c_off + c0 + i < D1) atomicAdd(a.S + ((size_t)q * K + k) * D1 + a.c_off + c0 + i, v[i]);
           }
         }
         umma::fence_before_sync();
