@@ -13,19 +13,21 @@
 //   * A = V_q^T is rebuilt by the same threads when the tuple changes (after the previous tile's MMAs);
 //   * epilogue as before: TMEM lane = embedding column c, Zc[cell][c] = Zo[cell][c] - D'[c][cell], coalesced
 //     across the warp; one warp pair per accumulator, tile records fetched one tile ahead.
-// Warp roles (448 threads): 0 MMA issuer, 2-5 loaders / converters, 6-9 / 10-13 epilogue of accumulator 0 / 1 (a warp
-// serves TMEM lane quarter warp % 4 = 32 embedding columns; quarters beyond d idle).  Limits per launch: d <= 128 and
+// Warp roles (576 threads): 0 MMA issuer; 2, 3, 6, 7 loaders / converters; epilogue warps serve TMEM lane quarter
+// warp % 4 (= 32 embedding columns) of one accumulator, for d <= 64 split further into two cell halves (eight warps).  Limits per launch: d <= 128 and
 // <= 112 clusters (shared memory); more clusters run as several launches over cluster ranges, each subtracting its
 // share from the partial result (the first from Zo).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace hb {
 
 constexpr int AP_TN = 64;         // cells per tile (= UMMA N), equals the static tile size TM
-constexpr int AP_THREADS = 448;   // 14 warps
-constexpr int AP_LOAD = 128;      // loader / converter threads (warps 2-5)
+constexpr int AP_THREADS = 576;   // 18 warps
+constexpr int AP_LOAD = 128;      // loader / converter threads (warps 2, 3, 6, 7)
 constexpr int AP_MAXK = 112;      // clusters per launch: (2 x 128 + 4 x 64) x KD floats of operands must fit 227 KB
 
 struct ApplyTcArgs {
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
     }
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(t_full + i, 1);
-      umma::mbar_init(t_empty + i, 32 * nq);
+      umma::mbar_init(t_empty + i, 32 * nq * (nq <= 2 ? 2 : 1));
     }
     umma::fence_barrier_init();
   }
@@ -138,9 +140,9 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
         stamp(it, 7);
       }
     }
-  } else if (warp >= 2 && warp < 6) {
+  } else if (warp == 2 || warp == 3 || warp == 6 || warp == 7) {
     // =============================== loaders / converters ===============================
-    const int lt = tid - 64;             // 0..127
+    const int lt = (warp < 4 ? warp - 2 : warp - 4) * 32 + lane;   // 0..127
     const int cell = lt & (AP_TN - 1);   // row of the tile
     const int half = lt >> 6;            // which half of the row's 16-byte pieces
     const int hsplit = (R4 + 1) >> 1;
@@ -230,50 +232,85 @@ __global__ void __launch_bounds__(AP_THREADS, 1) k_apply_tc(ApplyTcArgs a) {
       meta(it + 4, mc[3], ml[3], mq[3]);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp >= 6 && (warp & 3) < nq) {
-    // =============================== epilogue (warps 6-9: accumulator 0, 10-13: accumulator 1) ===============================
-    const int es = (warp >= 10) ? 1 : 0;     // accumulator served by this warp
-    const int wq = warp & 3;                 // TMEM lane quarter (hardware: warp % 4)
-    const int c = wq * 32 + lane;            // embedding column = TMEM lane
-    int use = 0;
-    int cell0_n = 0, len_n = 0;
-    if (t_begin + es < t_end) {
-      cell0_n = __ldg(a.tile_cell0 + t_begin + es);
-      len_n = __ldg(a.tile_len + t_begin + es);
+  } else {
+    // =============================== epilogue ===============================
+    // A warp may only touch TMEM lane quarter warp % 4 (= 32 embedding columns).  d <= 64: four warps per accumulator,
+    // lane quarter x cell half (warps 4,5 / 12,13 -> accumulator 0, warps 8,9 / 16,17 -> accumulator 1); d > 64: one
+    // warp per accumulator and lane quarter (4,5,10,11 / 8,9,14,15), all 64 cells.
+    const int wq = warp & 3;  // TMEM lane quarter (hardware: warp % 4)
+    const bool split = nq <= 2;
+    int es = -1, half = 0;
+    if (split) {
+      if (warp == 4 || warp == 5) es = 0, half = 0;
+      else if (warp == 12 || warp == 13) es = 0, half = 1;
+      else if (warp == 8 || warp == 9) es = 1, half = 0;
+      else if (warp == 16 || warp == 17) es = 1, half = 1;
+    } else {
+      if (warp == 4 || warp == 5 || warp == 10 || warp == 11) es = 0;
+      else if (warp == 8 || warp == 9 || warp == 14 || warp == 15) es = 1;
     }
-    for (int tile = t_begin + es; tile < t_end; tile += 2, ++use) {
-      const int cell0 = cell0_n, len = len_n;
-      if (tile + 2 < t_end) {
-        cell0_n = __ldg(a.tile_cell0 + tile + 2);
-        len_n = __ldg(a.tile_len + tile + 2);
-      }
-      // the tile's Zo values do not depend on the MMA: fetch them while it runs
-      float zo[AP_TN];
-      if (c < d) {
-#pragma unroll
-        for (int j = 0; j < AP_TN; ++j) zo[j] = (j < len) ? ld_stream(a.minuend + (size_t)(cell0 + j) * DS + c) : 0.f;
-      }
-      umma::mbar_wait(t_full + es, use & 1);
-      umma::fence_after_sync();
-      if (lane == 0 && wq == 0) stamp(2 * use + es, 8);
-      const uint32_t trow = tmem + es * AP_TN + ((uint32_t)(wq * 32) << 16);
-      // 16 cells at a time (TMEM -> registers -> store): the whole accumulator would not fit beside zo[]
-#pragma unroll
-      for (int j = 0; j < AP_TN; j += 16) {
-        float t16[16];
-        umma::tmem_ld16(trow + j, t16);
-        umma::tmem_ld_wait();
-        if (j + 16 == AP_TN) {  // accumulator fully read -> the issuer may overwrite it
-          umma::fence_before_sync();
-          umma::mbar_arrive(t_empty + es);
+    if (es >= 0 && wq < nq) {
+      const int c = wq * 32 + lane;  // embedding column = TMEM lane
+      auto run = [&](auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;  // cells per warp and tile
+        const int j0 = half * NC;
+        int use = 0;
+        int cell0_n = 0, len_n = 0;
+        if (t_begin + es < t_end) {
+          cell0_n = __ldg(a.tile_cell0 + t_begin + es);
+          len_n = __ldg(a.tile_len + t_begin + es);
         }
-        if (c < d) {
+        for (int tile = t_begin + es; tile < t_end; tile += 2, ++use) {
+          const int cell0 = cell0_n, len = len_n;
+          if (tile + 2 < t_end) {
+            cell0_n = __ldg(a.tile_cell0 + tile + 2);
+            len_n = __ldg(a.tile_len + tile + 2);
+          }
+          // NC = 32: the tile's minuend values are fetched while the MMAs run and both TMEM loads of the warp's cells
+          // are in flight together; NC = 64 (d > 64): 16 cells at a time (registers)
+          constexpr int CH = (NC == 32) ? 32 : 16;
+          float zo[CH];
+          auto fetch = [&](int j) {
+            if (c < d) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (j + i < len) a.Zc[(size_t)(cell0 + j + i) * DS + c] = zo[j + i] - t16[i];
+              for (int i = 0; i < CH; ++i)
+                zo[i] = (j0 + j + i < len) ? ld_stream(a.minuend + (size_t)(cell0 + j0 + j + i) * DS + c) : 0.f;
+            }
+          };
+          if (NC == CH) fetch(0);
+          umma::mbar_wait(t_full + es, use & 1);
+          umma::fence_after_sync();
+          if (lane == 0 && wq == 0 && half == 0) stamp(2 * use + es, 8);
+          const uint32_t trow = tmem + es * AP_TN + j0 + ((uint32_t)(wq * 32) << 16);
+#pragma unroll
+          for (int j = 0; j < NC; j += CH) {
+            if (NC != CH) fetch(j);
+            float tv[CH];
+#pragma unroll
+            for (int u = 0; u < CH; u += 16) {
+              float t16[16];
+              umma::tmem_ld16(trow + j + u, t16);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) tv[u + i] = t16[i];
+            }
+            umma::tmem_ld_wait();
+            if (j + CH == NC) {  // this warp's part of the accumulator is read -> the issuer may overwrite it
+              umma::fence_before_sync();
+              umma::mbar_arrive(t_empty + es);
+            }
+            if (c < d) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i)
+                if (j0 + j + i < len) a.Zc[(size_t)(cell0 + j0 + j + i) * DS + c] = zo[i] - tv[i];
+            }
+          }
+          if (lane == 0 && wq == 0 && half == 0) stamp(2 * use + es, 9);
         }
-      }
-      if (lane == 0 && wq == 0) stamp(2 * use + es, 9);
+      };
+      if (split)
+        run(std::integral_constant<int, 32>());
+      else
+        run(std::integral_constant<int, 64>());
     }
   }
   umma::fence_before_sync();

@@ -31,6 +31,7 @@
 #include "update_kernel4.cuh"
 #include "update_kernel5.cuh"
 #include "assign_tc3.cuh"
+#include "logits_tc.cuh"
 #include "apply_tc3.cuh"
 #include "stats_tc3.cuh"
 
@@ -308,6 +309,7 @@ struct hb_handle {
   DevBuf<int> tc_cell0, tc_len, tc_tuple;  // 128-cell tiles of the tensor-core kernels
   int tc_ntiles = 0;
   bool use_tc_assign = false, use_tc_apply = false, use_tc_stats = false;
+  bool use_tc_logits = false;  // cold start of shapes outside the fused assignment kernel: logits_tc.cuh
   int kernel_set = 0;            // HB_KERNEL_SET test hook (bits HB_KS_*), read by hb_setup
   bool legacy_centroid = false;  // HB_LEGACY_CENTROID_STEP: centroid update at the top of every clustering round
   DevBuf<float> Rkeep, OEkeep;   // R / O,E saved around the distance-only assignment of that step
@@ -574,6 +576,48 @@ int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_o
     k_assign_finalize<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->Oacc.p, h->Oacc.p + (size_t)B * KS, h->Pr_b.p,
                                                                     h->O.p, h->E.p, B, K, KS);
     CKL();
+    return 0;
+  }
+  if (plan_mode && h->use_tc_logits) {
+    // shapes the fused kernel cannot hold (d > 64 or K > 128): logits per 64-cluster range on the tensor cores, then
+    // one gather pass over U in the order of round 0 for the softmax + the blocks' removal sums (harmony.cpp:312-313)
+    LogitsArgs t{};
+    t.Zc = h->Zc.p;
+    t.Y = h->Y.p;
+    t.sigma = h->sigma.p;
+    t.U = h->U.p;
+    t.n = h->n;
+    t.d = d;
+    t.K = K;
+    t.DS = h->DS;
+    t.KS = KS;
+    t.KD = (d + 7) & ~7;
+    t.normalise = normalise ? 1 : 0;
+    const size_t smem_lg = logits_smem_bytes(t.KD);
+    CK(cudaFuncSetAttribute(k_logits_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lg));
+    const int grid_lg = (int)std::max<int64_t>(1, std::min<int64_t>((h->n + LG_TM - 1) / LG_TM, h->num_sms));
+    for (t.n_off = 0; t.n_off < K; t.n_off += LG_NP) {
+      k_logits_tc<<<grid_lg, LG_THREADS, smem_lg, h->stream>>>(t);
+      CKL();
+    }
+    const size_t R0 = (size_t)h->plan_set * h->plan_rounds;
+    const int nv = upd4_nv(KS);
+    const size_t smem_sm = sizeof(float) * 8 * 128 * (size_t)nv;
+    if (nv == 1)
+      k_softmax_block_sums<1><<<dim3(h->coop_grid, h->nb), 256, smem_sm, h->stream>>>(
+          h->U.p, h->order.p + R0 * h->n, h->ranges.p + R0 * h->nb * h->coop_grid, h->tuple_levels.p, h->acc2.p, h->coop_grid, K, KS,
+          h->C, B);
+    else
+      k_softmax_block_sums<2><<<dim3(h->coop_grid, h->nb), 256, smem_sm, h->stream>>>(
+          h->U.p, h->order.p + R0 * h->n, h->ranges.p + R0 * h->nb * h->coop_grid, h->tuple_levels.p, h->acc2.p, h->coop_grid, K, KS,
+          h->C, B);
+    CKL();
+    h->R_user_set = false;
+    const size_t XH = (size_t)B * KS + KS;
+    if (h->world > 1) TRY(allreduce_f(h, h->acc2.p + 2 * XH, 2 * XH * (size_t)h->nb));
+    k_assign_finalize_plan<<<(B * KS + 255) / 256, 256, 0, h->stream>>>(h->acc2.p, h->nb, h->Pr_b.p, h->O.p, h->E.p, B, K, KS);
+    CKL();
+    h->zc_pending_norm = normalise;
     return 0;
   }
   if (plan_mode) return fail(h, 3, "internal: plan-order assignment without the tensor-core kernel");
@@ -1903,6 +1947,8 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
   h->assign_ns = assign3_smem_bytes(2, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit ? 2 : 1;
   h->use_tc_assign = (d <= 64) && (K <= 128) && assign3_smem_bytes(h->assign_ns, (d + 7) & ~7, (K + 15) & ~15, KS) <= smem_limit &&
                      !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
+  h->use_tc_logits = !h->use_tc_assign && (d <= 128) && logits_smem_bytes((d + 7) & ~7) <= smem_limit &&
+                     !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
   h->pt_cap = (size_t)N / TC_TM + (size_t)h->nb * J + 2;
   if (h->use_tc_assign && h->use_v4) {
     CK(h->pt_p0.alloc(2 * h->pt_cap));
@@ -2242,7 +2288,7 @@ int hb_cluster(hb_handle* h, const int64_t* update_orders) {
   const bool persistent = h->use_v2 && !h->legacy_centroid && (h->use_v4 || T <= 31);
   // The single-pass update kernel takes round 0's removal sums from the assignment step itself when that step
   // runs in plan order (tensor-core kernel); every other combination runs the assignment in natural order first.
-  const bool plan_assign = cold && persistent && h->use_v4 && h->use_tc_assign && T > 0;
+  const bool plan_assign = cold && persistent && h->use_v4 && (h->use_tc_assign || h->use_tc_logits) && T > 0;
   if (cold && !plan_assign) {
     TRY(run_assign(h, true, false, false));  // the cold start does not evaluate the objective
     CK(cudaMemsetAsync(h->obj_acc.p, 0, 2 * sizeof(double), h->stream));

@@ -117,6 +117,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
     const int kA = ct & 127, ccA = ct >> 7;   // A: cluster kA, cell chunks ccA + 2 i (i < 8)
     const int cB = ct & 63, ccB = ct >> 6;    // B: column cB,  cell chunks ccB + 4 i (i < 4)
     float vA[8][4], vB[4][4];
+    // operand pair of a value: hi = the value itself (the tensor core reads its upper 19 bits), lo = the remainder
+    // v - trunc_tf32(v), exact in fp32 and truncated by the tensor core in turn (relative error of the pair <= 2^-20)
+    auto split = [](float v, float& hi, float& lo) {
+      hi = v;
+      lo = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    };
     auto fetch = [&](int tile) {  // this thread's values of a tile, straight from global memory
       int cell0 = 0, len = 0;
       if (tile < t_end) {
@@ -156,10 +162,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float4 hi, lo;
-        umma::split_tf32(vA[i][0], hi.x, lo.x);
-        umma::split_tf32(vA[i][1], hi.y, lo.y);
-        umma::split_tf32(vA[i][2], hi.z, lo.z);
-        umma::split_tf32(vA[i][3], hi.w, lo.w);
+        split(vA[i][0], hi.x, lo.x);
+        split(vA[i][1], hi.y, lo.y);
+        split(vA[i][2], hi.z, lo.z);
+        split(vA[i][3], hi.w, lo.w);
         const int off = ((ccA + 2 * i) * 128 + kA) * 4;
         *reinterpret_cast<float4*>(ah + off) = hi;
         *reinterpret_cast<float4*>(al + off) = lo;
@@ -167,10 +173,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 hi, lo;
-        umma::split_tf32(vB[i][0], hi.x, lo.x);
-        umma::split_tf32(vB[i][1], hi.y, lo.y);
-        umma::split_tf32(vB[i][2], hi.z, lo.z);
-        umma::split_tf32(vB[i][3], hi.w, lo.w);
+        split(vB[i][0], hi.x, lo.x);
+        split(vB[i][1], hi.y, lo.y);
+        split(vB[i][2], hi.z, lo.z);
+        split(vB[i][3], hi.w, lo.w);
         const int off = ((ccB + 4 * i) * 64 + cB) * 4;
         *reinterpret_cast<float4*>(bh + off) = hi;
         *reinterpret_cast<float4*>(bl + off) = lo;
