@@ -123,12 +123,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
       hi = v;
       lo = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     };
-    auto fetch = [&](int tile) {  // this thread's values of a tile, straight from global memory
-      int cell0 = 0, len = 0;
+    // tile records (first cell, cells, tuple) run two tiles ahead of the value loads, the value loads one tile ahead of
+    // the conversion: no load that feeds an address or a branch is waited for
+    auto meta = [&](int tile, int& cell0, int& len, int& q) {
+      cell0 = 0;
+      len = 0;
+      q = -1;
       if (tile < t_end) {
         cell0 = __ldg(a.tile_cell0 + tile);
         len = __ldg(a.tile_len + tile);
+        q = __ldg(a.tile_tuple + tile);
       }
+    };
+    auto fetch = [&](int cell0, int len) {  // this thread's values of a tile, straight from global memory
       const float* rR = a.R + (size_t)cell0 * KS + a.k_off + kA;
       const float* rZ = a.Zo + (size_t)cell0 * DS + a.c_off + cB;
 #pragma unroll
@@ -148,11 +155,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
           vB[i][j] = v;
         }
     };
-    fetch(t_begin);
+    int c0_0, len0, q0, c0_1, len1, q1, c0_2, len2, q2;
+    meta(t_begin, c0_0, len0, q0);
+    meta(t_begin + 1, c0_1, len1, q1);
+    meta(t_begin + 2, c0_2, len2, q2);
+    fetch(c0_0, len0);
     int it = 0, runs = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-      const int q = a.tile_tuple[tile];
-      const bool last_of_run = (tile + 1 == t_end) || (a.tile_tuple[tile + 1] != q);
+      const int q = q0;
+      const bool last_of_run = q1 != q;  // q1 = -1 beyond the CTA's last tile
       const int s = it & 1;
       if (it >= 2) umma::mbar_wait(ab_empty + s, ((it >> 1) - 1) & 1);  // MMAs of tile it - 2 are done with the stage
       float* ah = Ahi + s * A_ST;
@@ -183,7 +194,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_stats_tc(StatsTcArgs a) {
       }
       umma::fence_proxy_async();
       umma::mbar_arrive(ab_full + s);
-      fetch(tile + 1);  // the next tile's values travel while this one is multiplied
+      fetch(c0_1, len1);  // the next tile's values travel while this one is multiplied
+      c0_0 = c0_1, len0 = len1, q0 = q1;
+      c0_1 = c0_2, len1 = len2, q1 = q2;
+      meta(tile + 3, c0_2, len2, q2);
       if (last_of_run && warp < 8) {
         // flush the accumulator of this tuple: thread = cluster row (TMEM lane), 64 columns
         umma::mbar_wait(acc_full, runs & 1);
