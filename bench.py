@@ -211,8 +211,9 @@ def cpu_sample_cells():
     return int(max(20_000, min(200_000, 200_000 * (100 * 50) / (W["K"] * W["d"]))))
 
 
-def cpu_reference_run(n_cells, iters, threads, seed=20260925):
-    """Times the CPU oracle (restatement of the reference's Armadillo/OpenBLAS path) on host cores."""
+def cpu_reference_run(n_cells, iters, threads, seed=20260925, keep=None):
+    """Times the CPU oracle (restatement of the reference's Armadillo/OpenBLAS path) on host cores.  `keep` (a dict)
+    receives the inputs and the oracle's final state so that the caller can hold the GPU path against them."""
     from oracle.oracle import OracleHarmony, load_blas
     blas = load_blas(threads)
     Z, b = synth_shard(n_cells, 0, seed)
@@ -223,16 +224,44 @@ def cpu_reference_run(n_cells, iters, threads, seed=20260925):
     o.setup(Z, kw["phi"], kw["B_vec"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, 1e-5)
     o.init_cluster_cpp(Y0)
     rng = np.random.default_rng(5)
-    times = []
+    times, all_perms = [], []
     for it in range(iters + 1):             # iteration 1 skips the cold start -> untimed
         perms = np.stack([rng.permutation(n_cells) for _ in range(T)]).astype(np.int64)
+        all_perms.append(perms)
         t0 = time.perf_counter()
         o.cluster_cpp(perms)
         o.moe_correct_ridge_cpp()
         o.check_convergence(1)
         if it > 0:
             times.append(time.perf_counter() - t0)
+    if keep is not None:
+        keep.update(Z=Z, kw=kw, Y0=Y0, perms=all_perms, Z_corr=o.get("Z_corr"), R=o.get("R"))
     return float(np.median(times)), blas
+
+
+def parity_on_sample(keep, device):
+    """The GPU path on the CPU leg's sample (same centroids, same update orders): rel-L2 of the corrected embedding
+    and the number of cells whose hard cluster index differs from the fp32 reference-order oracle's."""
+    from harmony_b200.harmony import harmony
+    kw = keep["kw"]
+    g = harmony(device=device)
+    g.setup(keep["Z"], kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, W["K"], 0.05, kw["B_vec"],
+            kw["cutoff"])
+    g.init_cluster_cpp(keep["Y0"])
+    for perms in keep["perms"]:
+        assert g.cluster_cpp(perms) == 0
+        g.moe_correct_ridge_cpp()
+        g.check_convergence(1)
+    Zg, Rg = g.getZcorr().T, g.R.T
+    Zo, Ro = keep["Z_corr"], keep["R"]
+    part = np.partition(Ro, -2, axis=1)
+    gap = part[:, -1] - part[:, -2]
+    diff = Rg.argmax(axis=1) != Ro.argmax(axis=1)
+    return {"cells": int(Zo.shape[0]), "iterations": len(keep["perms"]),
+            "rel_l2_Z_vs_oracle32": float(np.linalg.norm(Zg - Zo) / np.linalg.norm(Zo)),
+            "argmax_mismatch": int(diff.sum()),
+            "argmax_mismatch_largest_oracle_top2_gap": float(gap[diff].max()) if diff.any() else 0.0,
+            "max_abs_dR": float(np.abs(Rg - Ro).max())}
 
 
 def run_reference(args):
@@ -439,7 +468,7 @@ def main():
         g2.setup(Zp, kw["phi"], kw["sigma"], kw["theta"], None, kw["alpha"], T, 1e-3, -np.inf, K, 0.05, kw["B_vec"],
                  kw["cutoff"])
         g2.set_seed(1234)
-        g2.init_cluster_cpp(Y0)
+        g2.init_cluster_cpp()                            # native kmeans_centers (utils.cpp:10-64), like RunHarmony()
         for _ in range(iters_e2e):
             step(g2)
         out = g2.getZcorr()
@@ -454,17 +483,21 @@ def main():
                "h2d_bytes_per_step": int((Z.nbytes + kw["phi"].nbytes) * world / iters_e2e),
                "d2h_bytes_per_step": int(out.nbytes * world / iters_e2e),
                "iterations": iters_e2e, "seconds": t_e2e,
-               "what": "harmony() + setup (H2D, pinned host Z fp64) + init_cluster_cpp + 10 x harmonize body + "
-                       "getZcorr (D2H fp64); bytes are per iteration (totals / 10)"}
+               "what": "harmony() + setup (H2D, pinned host Z fp64) + init_cluster_cpp with the NATIVE k-means "
+                       "initialisation + 10 x harmonize body + getZcorr (D2H fp64); bytes are per iteration (totals / 10)"}
         del g2
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_sample = cpu_sample_cells()
-        t_iter, blas = cpu_reference_run(n_sample, 2, 1)
+        keep = {}
+        t_iter, blas = cpu_reference_run(n_sample, 2, 1, keep=keep)
         cpu = {"value": n_sample / t_iter, "unit": "cells/s/iter", "cores": 1, "kind": "port",
                "sample": f"{n_sample} cells x {D} PCs, K={K}, levels {W['B_vec']}, 2 timed iterations, single thread "
                          f"(reference default ncores=1), sgemm from {os.path.basename(blas)}"}
+        # the same sample through the GPU path, held against the oracle's result (the oracle as the checker)
+        parity = parity_on_sample(keep, local_rank)
+        del keep
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "cells/s/iter", "n_gpus": world, "steps": args.steps,
@@ -484,7 +517,7 @@ def main():
                                   "frac": step_ach / peaks["hbm_gbs"],
                                   "algorithmic_bytes_per_cell_iter": ALGO_BYTES_PER_CELL_ITER},
                 "regions_ms_per_step": {r: round(v["ms_per_step"], 4) for r, v in reg.items()},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

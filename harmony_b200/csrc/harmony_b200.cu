@@ -452,6 +452,31 @@ int dispatch_kq(hb_handle* h, int K, F&& f) {
   return fail(h, 2, "K = %d is not supported (K <= 1024)", K);
 }
 
+// U[i][k] = (2 / sigma_k) (z_i . y_k / |z_i| - 1) for all clusters on the tensor cores, 64 clusters per launch
+// (logits_tc.cuh); `sigma`: device array of K values
+int launch_logits(hb_handle* h, const float* sigma, bool normalise) {
+  LogitsArgs t{};
+  t.Zc = h->Zc.p;
+  t.Y = h->Y.p;
+  t.sigma = sigma;
+  t.U = h->U.p;
+  t.n = h->n;
+  t.d = h->d;
+  t.K = h->K;
+  t.DS = h->DS;
+  t.KS = h->KS;
+  t.KD = (h->d + 7) & ~7;
+  t.normalise = normalise ? 1 : 0;
+  const size_t smem_lg = logits_smem_bytes(t.KD);
+  CK(cudaFuncSetAttribute(k_logits_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lg));
+  const int grid_lg = (int)std::max<int64_t>(1, std::min<int64_t>((h->n + LG_TM - 1) / LG_TM, h->num_sms));
+  for (t.n_off = 0; t.n_off < h->K; t.n_off += LG_NP) {
+    k_logits_tc<<<grid_lg, LG_THREADS, smem_lg, h->stream>>>(t);
+    CKL();
+  }
+  return 0;
+}
+
 // ---- K1 launcher: assignment from centroids (init + cold start) -------------------------------
 // plan_mode: tiles follow round 0 of the current plan set (tensor-core kernel only); want_obj: objective sums (init)
 int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_obj = true) {
@@ -581,25 +606,7 @@ int run_assign(hb_handle* h, bool normalise, bool plan_mode = false, bool want_o
   if (plan_mode && h->use_tc_logits) {
     // shapes the fused kernel cannot hold (d > 64 or K > 128): logits per 64-cluster range on the tensor cores, then
     // one gather pass over U in the order of round 0 for the softmax + the blocks' removal sums (harmony.cpp:312-313)
-    LogitsArgs t{};
-    t.Zc = h->Zc.p;
-    t.Y = h->Y.p;
-    t.sigma = h->sigma.p;
-    t.U = h->U.p;
-    t.n = h->n;
-    t.d = d;
-    t.K = K;
-    t.DS = h->DS;
-    t.KS = KS;
-    t.KD = (d + 7) & ~7;
-    t.normalise = normalise ? 1 : 0;
-    const size_t smem_lg = logits_smem_bytes(t.KD);
-    CK(cudaFuncSetAttribute(k_logits_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lg));
-    const int grid_lg = (int)std::max<int64_t>(1, std::min<int64_t>((h->n + LG_TM - 1) / LG_TM, h->num_sms));
-    for (t.n_off = 0; t.n_off < K; t.n_off += LG_NP) {
-      k_logits_tc<<<grid_lg, LG_THREADS, smem_lg, h->stream>>>(t);
-      CKL();
-    }
+    TRY(launch_logits(h, h->sigma.p, normalise));
     const size_t R0 = (size_t)h->plan_set * h->plan_rounds;
     const int nv = upd4_nv(KS);
     const size_t smem_sm = sizeof(float) * 8 * 128 * (size_t)nv;
@@ -1251,6 +1258,34 @@ int run_update_v2(hb_handle* h, int T, int t0, int t1, unsigned write_mask) {
 }
 
 
+// S[q][k][:] += R_q^T [Z_q | 1] on the tensor cores (stats_tc3.cuh): one launch per 128 clusters x 64 columns of [Z | 1]
+// (K = 100, d = 50: one launch).  The caller zeroes S.
+int run_stats_tc(hb_handle* h, const float* Zsrc) {
+  const int K = h->K, D1 = h->d + 1;
+  StatsTcArgs t;
+  t.R = h->R.p;
+  t.Zo = Zsrc;
+  t.tile_cell0 = h->tile_cell0.p;
+  t.tile_len = h->tile_len.p;
+  t.tile_tuple = h->tile_tuple.p;
+  t.S = h->S.p;
+  t.ntiles = h->ntiles;
+  t.d = h->d;
+  t.K = K;
+  t.KS = h->KS;
+  t.DS = h->DS;
+  t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
+  const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
+  const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
+  CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+  for (t.k_off = 0; t.k_off < K; t.k_off += 128)
+    for (t.c_off = 0; t.c_off < D1; t.c_off += 64) {
+      k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
+      CKL();
+    }
+  return 0;
+}
+
 // ---- moe_correct_ridge_cpp (harmony.cpp:345-638) -------------------------------------------------
 int run_correct(hb_handle* h) {
   const int K = h->K, d = h->d, B = h->B, J = h->J, C = h->C;
@@ -1259,28 +1294,7 @@ int run_correct(hb_handle* h) {
     RegionScope rs(h, "ridge_stats");
     CK(cudaMemsetAsync(h->S.p, 0, sizeof(float) * (size_t)J * K * D1, h->stream));
     if (h->use_tc_stats) {
-      StatsTcArgs t;
-      t.R = h->R.p;
-      t.Zo = h->Zo.p;
-      t.tile_cell0 = h->tile_cell0.p;
-      t.tile_len = h->tile_len.p;
-      t.tile_tuple = h->tile_tuple.p;
-      t.S = h->S.p;
-      t.ntiles = h->ntiles;
-      t.d = d;
-      t.K = K;
-      t.KS = h->KS;
-      t.DS = h->DS;
-      t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
-      const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
-      const size_t smem_tc = stats_tc_smem_bytes(h->KS, h->DS);
-      CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-      // one launch per 128 clusters x 64 columns of [Zo | 1] (K = 100, d = 50: one launch)
-      for (t.k_off = 0; t.k_off < K; t.k_off += 128)
-        for (t.c_off = 0; t.c_off < D1; t.c_off += 64) {
-          k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
-          CKL();
-        }
+      TRY(run_stats_tc(h, h->Zo.p));
     } else {
     StatsArgs a;
       a.R = h->R.p;
@@ -2110,10 +2124,24 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
       cells[k] = (int64_t)std::floor((double)kmeans_uniform(seed, (uint64_t)K, (uint64_t)k) * (double)(h->N_global - 1));
     TRY(gather(-1));
     // (2) the races of all centroids in one pass over the cells (a centroid's race only looks at its own start cell)
+    // both steps run from tensor-core logits U = 2 (z . y - 1) (k_logits_tc, sigma = 1) when that kernel takes the
+    // shape; else from the FFMA kernels (thread per cell)
+    const bool tc_init = (d <= 128) && logits_smem_bytes((d + 7) & ~7) <= (size_t)227 * 1024 - 256 && h->KS <= 256 &&
+                         !(h->kernel_set & HB_KS_FFMA_CONTRACTIONS);
+    DevBuf<float> ones, yy;
+    if (tc_init) {
+      CK(ones.alloc(K));
+      CK(yy.alloc(K));
+      k_fill_f<<<1, 256, 0, h->stream>>>(ones.p, (int64_t)K, 1.0f);
+      CKL();
+    }
     const size_t smem_pp = sizeof(float) * Kd;
-    if (smem_pp > 200 * 1024) return fail(h, 2, "K*d too large for the native k-means initialisation; pass Y0");
-    CK(cudaFuncSetAttribute(k_kmeans_race, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pp));
+    if (!tc_init) {
+      if (smem_pp > 200 * 1024) return fail(h, 2, "K*d too large for the native k-means initialisation; pass Y0");
+      CK(cudaFuncSetAttribute(k_kmeans_race, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pp));
+    }
     std::vector<unsigned long long> best(K);
+    bool logits_of_start = false;  // U holds the logits of the start cells
     auto race = [&](int i0, int i1, const std::vector<int64_t>& taken) -> int {
       DevBuf<int64_t> taken_d;
       if (!taken.empty()) {
@@ -2121,10 +2149,25 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
         CK(cudaMemcpyAsync(taken_d.p, taken.data(), sizeof(int64_t) * taken.size(), cudaMemcpyHostToDevice, h->stream));
       }
       CK(cudaMemsetAsync(best_d.p + i0, 0xff, sizeof(unsigned long long) * (i1 - i0), h->stream));
-      k_kmeans_race<<<grid_for(h->n, 128, h->num_sms * 4), 128, sizeof(float) * (size_t)(i1 - i0) * d, h->stream>>>(
-          h->Zc.p, h->sort_perm.p, h->Y.p, best_d.p, taken.empty() ? nullptr : taken_d.p, (int)taken.size(), h->n, K, d, h->DS,
-          h->cell_offset, seed, i0, i1);
-      CKL();
+      if (tc_init) {
+        if (!logits_of_start) {
+          TRY(launch_logits(h, ones.p, false));
+          logits_of_start = true;
+        }
+        const int grid_r = grid_for(h->n * 32, 256, h->num_sms * 8);
+        if (upd4_nv(h->KS) == 1)
+          k_kmeans_race_u<1><<<grid_r, 256, 0, h->stream>>>(h->U.p, h->sort_perm.p, best_d.p, taken.empty() ? nullptr : taken_d.p,
+                                                          (int)taken.size(), h->n, K, h->KS, h->cell_offset, seed, i0, i1);
+        else
+          k_kmeans_race_u<2><<<grid_r, 256, 0, h->stream>>>(h->U.p, h->sort_perm.p, best_d.p, taken.empty() ? nullptr : taken_d.p,
+                                                          (int)taken.size(), h->n, K, h->KS, h->cell_offset, seed, i0, i1);
+        CKL();
+      } else {
+        k_kmeans_race<<<grid_for(h->n, 128, h->num_sms * 4), 128, sizeof(float) * (size_t)(i1 - i0) * d, h->stream>>>(
+            h->Zc.p, h->sort_perm.p, h->Y.p, best_d.p, taken.empty() ? nullptr : taken_d.p, (int)taken.size(), h->n, K, d, h->DS,
+            h->cell_offset, seed, i0, i1);
+        CKL();
+      }
       if (h->world > 1) CKN(g_nccl.AllReduce(best_d.p + i0, best_d.p + i0, (size_t)(i1 - i0), ncclUint64, ncclMin, h->comm, h->stream));
       CK(cudaMemcpyAsync(best.data() + i0, best_d.p + i0, sizeof(unsigned long long) * (i1 - i0), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
@@ -2148,9 +2191,26 @@ int hb_init_cluster(hb_handle* h, const double* Y0) {
     h->kmeans_cells = cells;
     TRY(gather(-1));
     const size_t smem = sizeof(float) * Kd;
-    if (smem > 200 * 1024) return fail(h, 2, "K*d too large for the native k-means initialisation; pass Y0");
-    CK(cudaFuncSetAttribute(k_kmeans_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!tc_init) CK(cudaFuncSetAttribute(k_kmeans_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int iter = 0; iter < 10; ++iter) {
+      if (tc_init) {
+        // Lloyd iteration on the tensor cores: logits -> one-hot rows of R -> members' sums and counts (K3) -> means
+        TRY(launch_logits(h, ones.p, false));
+        k_kmeans_norms<<<(K + 127) / 128, 128, 0, h->stream>>>(h->Y.p, yy.p, K, d);
+        CKL();
+        const int grid_p = grid_for(h->n * 32, 256, h->num_sms * 8);
+        if (upd4_nv(h->KS) == 1)
+          k_kmeans_pick<1><<<grid_p, 256, 0, h->stream>>>(h->U.p, yy.p, h->R.p, h->n, K, h->KS);
+        else
+          k_kmeans_pick<2><<<grid_p, 256, 0, h->stream>>>(h->U.p, yy.p, h->R.p, h->n, K, h->KS);
+        CKL();
+        CK(cudaMemsetAsync(h->S.p, 0, sizeof(float) * (size_t)h->J * K * (d + 1), h->stream));
+        TRY(run_stats_tc(h, h->Zc.p));
+        TRY(allreduce_f(h, h->S.p, (size_t)h->J * K * (d + 1)));
+        k_kmeans_means_from_stats<<<(int)((Kd + 255) / 256), 256, 0, h->stream>>>(h->S.p, h->Y.p, h->J, K, d);
+        CKL();
+        continue;
+      }
       CK(cudaMemsetAsync(ysum.p, 0, sizeof(float) * (Kd + K), h->stream));
       k_kmeans_assign<<<grid_for(h->n, 128, h->num_sms * 4), 128, smem, h->stream>>>(h->Zc.p, h->Y.p, ysum.p, ysum.p + Kd,
                                                                                        h->n, K, d, h->DS);
@@ -2185,27 +2245,7 @@ int legacy_centroid_step(hb_handle* h) {
   const size_t nK = (size_t)h->n * KS, BK = (size_t)B * KS;
   CK(cudaMemsetAsync(h->S.p, 0, sizeof(float) * (size_t)J * K * D1, h->stream));
   if (h->use_tc_stats) {
-    StatsTcArgs t;
-    t.R = h->R.p;
-    t.Zo = h->Zc.p;  // the statistics of the corrected, normalised embedding
-    t.tile_cell0 = h->tile_cell0.p;
-    t.tile_len = h->tile_len.p;
-    t.tile_tuple = h->tile_tuple.p;
-    t.S = h->S.p;
-    t.ntiles = h->ntiles;
-    t.d = d;
-    t.K = K;
-    t.KS = KS;
-    t.DS = h->DS;
-    t.tiles_per_cta = std::max(1, (h->ntiles + h->num_sms - 1) / h->num_sms);
-    const int grid_tc = (h->ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
-    const size_t smem_tc = stats_tc_smem_bytes(KS, h->DS);
-    CK(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-    for (t.k_off = 0; t.k_off < K; t.k_off += 128)
-      for (t.c_off = 0; t.c_off < D1; t.c_off += 64) {
-        k_stats_tc<<<grid_tc, ST_THREADS, smem_tc, h->stream>>>(t);
-        CKL();
-      }
+    TRY(run_stats_tc(h, h->Zc.p));  // the statistics of the corrected, normalised embedding
   } else {
     StatsArgs a;
     a.R = h->R.p;

@@ -167,6 +167,128 @@ __global__ void __launch_bounds__(128) k_kmeans_race(const float* __restrict__ Z
     }
   }
 }
+// ---- the same two steps fed by tensor-core logits U[i][k] = 2 (z_i . y_k - 1) (k_logits_tc with sigma = 1) ----
+// Race of initialize_centroids from the logits of the START cells: |U[i][k]| is the distance |2 (1 - y_k . x_i)| of
+// utils.cpp:27.  One warp per row (lane l owns the 16-byte pieces l, l + 32, ..), running minima per column in
+// registers, one atomicMin per column and warp at the end.  Centroids outside [i0, i1) and cells in `taken` sit out.
+template <int NV>
+__global__ void __launch_bounds__(256) k_kmeans_race_u(const float* __restrict__ U, const int* __restrict__ sort_perm,
+                                                       unsigned long long* __restrict__ best, const int64_t* __restrict__ taken,
+                                                       int ntaken, int64_t n, int K, int KS, int64_t cell_offset, uint64_t seed,
+                                                       int i0, int i1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int KS4 = KS >> 2;
+  unsigned long long mn[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mn[v][c] = ~0ull;
+  for (int64_t s = gw; s < n; s += nw) {
+    const uint64_t g = (uint64_t)(cell_offset + sort_perm[s]);
+    bool free_cell = true;
+    for (int e = 0; e < ntaken && free_cell; ++e) free_cell = (uint64_t)taken[e] != g;
+    if (!free_cell) continue;  // warp-uniform
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (lane + 32 * v >= KS4) continue;
+      const float4 u = ld_stream4(reinterpret_cast<const float4*>(U + (size_t)s * KS) + lane + 32 * v);
+      const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 4 * (lane + 32 * v) + c;
+        if (i >= i0 && i < i1 && i < K) {
+          const float p = -logf(kmeans_uniform(seed, (uint64_t)i, g)) / fabsf(uu[c]);  // dist == 0: +inf, never the minimum
+          const unsigned long long key = ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(g & 0xffffffffull);
+          mn[v][c] = key < mn[v][c] ? key : mn[v][c];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 4 * (lane + 32 * v) + c;
+      if (i < K && mn[v][c] != ~0ull) atomicMin(best + i, mn[v][c]);
+    }
+}
+// |y_k|^2 of the current means
+__global__ void k_kmeans_norms(const float* __restrict__ Y, float* __restrict__ yy, int K, int d) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int c = 0; c < d; ++c) s = fmaf(Y[(size_t)k * d + c], Y[(size_t)k * d + c], s);
+  yy[k] = s;
+}
+// Lloyd assignment from the logits: nearest mean in Euclidean distance = argmax_k (2 z.y_k - |y_k|^2) = argmax_k
+// (U[i][k] - |y_k|^2) (ties: the lower k), written as a one-hot row of R — the statistics kernel (K3) then yields the
+// members' sums and counts of every mean on the tensor cores.  One warp per row.
+template <int NV>
+__global__ void __launch_bounds__(256) k_kmeans_pick(const float* __restrict__ U, const float* __restrict__ yy,
+                                                     float* __restrict__ R, int64_t n, int K, int KS) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int KS4 = KS >> 2;
+  float ny[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = 4 * (lane + 32 * v) + c;
+      ny[v][c] = (k < K) ? yy[k] : 0.f;
+    }
+  for (int64_t s = gw; s < n; s += nw) {
+    float bv = -3.0e38f;
+    int bk = 0x7fffffff;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (lane + 32 * v >= KS4) continue;
+      const float4 u = ld_stream4(reinterpret_cast<const float4*>(U + (size_t)s * KS) + lane + 32 * v);
+      const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = 4 * (lane + 32 * v) + c;
+        const float sc = uu[c] - ny[v][c];
+        if (k < K && sc > bv) {  // ascending k within the lane: a tie keeps the lower k
+          bv = sc;
+          bk = k;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      if (ov > bv || (ov == bv && ok < bk)) {
+        bv = ov;
+        bk = ok;
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (lane + 32 * v >= KS4) continue;
+      const int k0 = 4 * (lane + 32 * v);
+      *reinterpret_cast<float4*>(R + (size_t)s * KS + k0) =
+          make_float4(bk == k0 ? 1.f : 0.f, bk == k0 + 1 ? 1.f : 0.f, bk == k0 + 2 ? 1.f : 0.f, bk == k0 + 3 ? 1.f : 0.f);
+    }
+  }
+}
+// means from the statistics S[q][k][0..d] (sums of the members per tuple, column d = their number): means without
+// members stay where they are (arma::kmeans keep_existing; Armadillo's dead-mean heuristic is not restated)
+__global__ void k_kmeans_means_from_stats(const float* __restrict__ S, float* __restrict__ Y, int J, int K, int d) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * d) return;
+  const int k = idx / d, c = idx - k * d;
+  const int D1 = d + 1;
+  float sum = 0.f, cnt = 0.f;
+  for (int q = 0; q < J; ++q) {
+    sum += S[((size_t)q * K + k) * D1 + c];
+    cnt += S[((size_t)q * K + k) * D1 + d];
+  }
+  if (cnt > 0.f) Y[idx] = sum / cnt;
+}
+
 // one Lloyd assignment pass on the cosine-normalised cells: nearest centroid by largest dot product,
 // accumulate per-cluster sums and counts.  Thread per cell, centroids in shared memory.
 __global__ void __launch_bounds__(128) k_kmeans_assign(const float* __restrict__ Zc, const float* __restrict__ Y,
