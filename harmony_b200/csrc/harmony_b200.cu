@@ -326,6 +326,7 @@ struct hb_handle {
   DevBuf<int> pt_p0, pt_len, pt_tuple, pt_blk, pt_count, pt_base;  // [2 sets] 128-row tiles of round 0 in plan order
   size_t pt_cap = 0;
   DevBuf<float> remT;    // [2][nb][J][KS] next round's removal sums per (block, tuple)
+  DevBuf<float> remS;    // [nb][J][KS] sharded cells: the ranks' remT of one round, summed
   DevBuf<int> next_at, chunk_q0, chunk_nq;
   DevBuf<int> lvl_ptr, lvl_tup;  // CSR level -> tuples (+ one trailing word: B_vec[0])
   int ntiles = 0, nchunks = 0;  // nchunks includes the trailing empty chunk
@@ -1063,6 +1064,7 @@ Upd4Args make_upd4_args(hb_handle* h, int T) {
   a.ring = h->ring.p;
   a.acc = h->acc2.p;
   a.remT = remT_ptr(h);
+  a.remS = h->remS.p;
   a.OEend = h->OEend.p;
   a.obj = h->obj2.p;
   a.bar = h->bar.p;
@@ -1994,6 +1996,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     CK(h->acc2.alloc(2 * (BK + KS) * ((size_t)Tplan * h->nb + 2)));
     CK(h->Psave.alloc(h->use_v4 ? 1 : 2 * (size_t)h->nb * BK));
     if (h->use_v4) CK(h->remT.alloc(2 * (size_t)h->nb * J * KS));
+    if (h->use_v4 && h->world > 1) CK(h->remS.alloc((size_t)h->nb * J * KS));
     CK(h->OEend.alloc((size_t)Tplan * 2 * BK));
     CK(h->obj2.alloc(2 * (size_t)Tplan));
     CK(h->bar.alloc(2 * ((size_t)Tplan * h->nb + 2)));

@@ -43,6 +43,7 @@ struct Upd4Args {
   float* ring;           // [2 parity][2 (O,E)][B][KS]
   float* acc;            // [(S+2)][SL]  slot(s) at (s+1)*SL: [add_O B*KS | add_rs KS | rem_O B*KS | rem_rs KS]
   float* remT;           // [2 parity][nb][J][KS]
+  float* remS;           // [nb][J][KS]  sharded cells: sum of the ranks' remT of the round being folded
   float* OEend;          // [T][2][B][KS]  tables at the end of each round (for the objective)
   double* obj;           // [T][2]
   unsigned* bar;         // cntU[s + 1] for s = -1 .. S, then cntF[t] for t = 0 .. T
@@ -85,6 +86,13 @@ __device__ __forceinline__ uint2 u4_ld_ll(const uint2* p) {
 }
 __device__ __forceinline__ void u4_st_ll(uint2* p, float val, unsigned epoch) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(epoch) : "memory");
+}
+// two consecutive words in one 16-byte store (p 16-byte aligned): each 64-bit element is single-copy atomic and
+// carries its own epoch, so the pair needs no atomicity as a whole — half the packets on the fabric
+__device__ __forceinline__ void u4_st_ll2(uint2* p, float v0, float v1, unsigned epoch) {
+  const unsigned long long w0 = ((unsigned long long)epoch << 32) | __float_as_uint(v0);
+  const unsigned long long w1 = ((unsigned long long)epoch << 32) | __float_as_uint(v1);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
 // sum over the ranks' entries of element `off` of the add half of accumulator slot index `sl`, in rank order
 // (waits for entries that have not arrived yet)
@@ -207,23 +215,17 @@ __global__ void __launch_bounds__(256) k_rem_sums(const float* __restrict__ R, c
 // round t's accumulator slots, one (block j, cluster k) column per call: rem_O[b][k] = sum over the tuples that
 // contain level b, in ascending tuple order (the same order on every rank and in every launch mode); the row sum is
 // the sum over the levels of covariate 0 (every tuple has exactly one).  Plain stores: the column has one owner.
-// world > 1: a tuple's value is the sum of the ranks' tables in rank order (peer memory).
-__device__ __forceinline__ void u4_fold_column(const Upd4Args& a, const Upd4Xch* x, int t, int j, int k) {
+// `table`: the [nb][J][KS] sums of round t — this rank's remT parity, or (sharded cells) the rank-ordered sum of all
+// ranks' tables that u4_gather_remT left in a.remS.
+__device__ __forceinline__ void u4_fold_column(const Upd4Args& a, const float* table, int t, int j, int k) {
   const int KS = a.KS, J = a.J, nb = a.nb, B = a.B;
   const int BK = B * KS, SL = 2 * (BK + KS);
-  const size_t joff = (size_t)(t & 1) * nb * J * KS + (size_t)j * J * KS + k;
+  const size_t joff = (size_t)j * J * KS + k;  // within `table` = the [nb][J][KS] sums of round t
   float* Tz = a.remT + (size_t)((t + 1) & 1) * nb * J * KS + (size_t)j * J * KS + k;
   float* slot = a.acc + (size_t)(t * nb + j + 1) * SL;
   float* rem_O = slot + BK + KS;
   float* rem_rs = rem_O + BK;
-  auto val = [&](int q) -> float {
-    if (x) {
-      float v = 0.f;
-      for (int r = 0; r < x->world; ++r) v += __ldcg(x->peer_remT[r] + joff + (size_t)q * KS);
-      return v;
-    }
-    return __ldcg(a.remT + joff + (size_t)q * KS);
-  };
+  auto val = [&](int q) -> float { return __ldcg(table + joff + (size_t)q * KS); };
   const int B0 = (a.C > 1) ? __ldg(a.lvl_first1) : B;  // levels of covariate 0 come first
   float rs = 0.f;
   for (int b0 = 0; b0 < B; b0 += 4) {  // four levels at a time: their loads are in flight together
@@ -249,8 +251,9 @@ __device__ __forceinline__ void u4_fold_column(const Upd4Args& a, const Upd4Xch*
 // Stand-alone fold (per-step launches: sharded cells without the peer exchange, where remT is all-reduced by the
 // host in between).  Same arithmetic as the in-kernel fold.
 __global__ void k_fold_round(Upd4Args a, int t) {
+  const float* table = a.remT + (size_t)(t & 1) * a.nb * a.J * a.KS;
   for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < a.nb * a.K; item += gridDim.x * blockDim.x)
-    u4_fold_column(a, nullptr, t, item / a.K, item % a.K);
+    u4_fold_column(a, table, t, item / a.K, item % a.K);
 }
 
 // After the last executed step S: O = O_S, E = E_S into the handle's tables.

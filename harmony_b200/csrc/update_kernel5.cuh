@@ -281,9 +281,9 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
     if (sh_last) {
       const float* src = a.acc + (size_t)sl * SL;  // complete: every CTA's atomics preceded its count
       const size_t entry = (size_t)sl * x.world + x.rank;
-      for (int i = tid; i < x.XH; i += U5_THREADS) {
-        const float v = __ldcg(src + i);
-        for (int r = 0; r < x.world; ++r) u4_st_ll(x.peer_inbox[r] + entry * x.XH + i, v, x.epoch);
+      for (int i = 2 * tid; i < x.XH; i += 2 * U5_THREADS) {  // XH is a multiple of 4: entries are 16-byte aligned
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(src + i));
+        for (int r = 0; r < x.world; ++r) u4_st_ll2(x.peer_inbox[r] + entry * x.XH + i, v.x, v.y, x.epoch);
       }
     }
   };
@@ -312,9 +312,37 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
     tv.KS = KS;
     return tv;
   };
+  unsigned* cntG = cntF + (a.T + 1);        // cntG[t]: the ranks' removal sums of round t are gathered
+  // sharded cells: the add half of slot index sl has started to arrive from every rank, i.e. every rank has finished
+  // the step that produced it (its last CTA pushes after all of the rank's CTAs counted)
+  auto wait_ranks = [&](int sl) {
+    if (tid < x.world) {
+      const uint2* w = x.inbox + ((size_t)sl * x.world + tid) * x.XH;
+      while (u4_ld_ll(w).y != x.epoch) __nanosleep(40);
+    }
+    __syncthreads();
+  };
+  // sharded cells: remS = sum over the ranks' remT tables of round t in rank order, 16 bytes per load (the peers'
+  // tables are read over NVLink: 4-byte loads per (tuple, cluster) swamp the fabric at 8 ranks)
+  auto gather_remT = [&](int t) {
+    const size_t par_off = (size_t)(t & 1) * nb * J * KS;
+    const int n4 = (nb * J * KS) >> 2;
+    for (int i = cta * U5_THREADS + tid; i < n4; i += grid * U5_THREADS) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < x.world; ++r) {
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(x.peer_remT[r] + par_off) + i);
+        v.x += p.x;
+        v.y += p.y;
+        v.z += p.z;
+        v.w += p.w;
+      }
+      reinterpret_cast<float4*>(a.remS)[i] = v;
+    }
+  };
   auto fold_round = [&](int t) {
+    const float* table = multi ? a.remS : a.remT + (size_t)(t & 1) * nb * J * KS;
     for (int item = cta * U5_THREADS + tid; item < nb * K; item += grid * U5_THREADS)
-      u4_fold_column(a, multi ? &x : nullptr, t, item / K, item % K);
+      u4_fold_column(a, table, t, item / K, item % K);
   };
 
   // objective partial sums of this lane.  Scalar sigma: accA = sum_rows (1/s) sum_k e u, accB = sum_rows (1/s) sum_k e log Psum
@@ -360,6 +388,12 @@ __global__ void __launch_bounds__(U5_THREADS, 1) k_update_steps5(Upd4Launch lp) 
       if (s > a.s_begin) wait_for(cntU + s - 1);  // add_{s-1}, ring(s-1); at j == 0 also: round t-1 is complete
       stamp(s, 7);
       if (j == 0 && t > 0) {
+        if (multi) {
+          wait_ranks(s + 1);  // add_{s-1} lives in slot index s + 1: every rank has finished round t - 1, its remT is final
+          gather_remT(t);
+          signal(cntG + t, -1);
+          wait_for(cntG + t);
+        }
         fold_round(t);
         signal(cntF + t, -1);
         wait_for(cntF + t);

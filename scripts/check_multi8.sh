@@ -12,14 +12,15 @@ run() {  # N config tag extra
   tail -2 gpurun_out/bench_$3.err
 }
 run 8 c3 8gpu_c3 ""
+run 8 c3 8gpu_c3_noplanoverlap "--kernel-set 16"
 run 8 c4 8gpu_c4 ""
 run 4 c3 4gpu_c3 ""
-run 8 c3 8gpu_c3_nccl "--kernel-set 8"
-timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_1gpu_c3_ref.json
-timeout 300 python bench.py --config c4 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_1gpu_c4_ref.json
+HB_TRACE_STEPS=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29523 \
+    bench.py --gpus 8 --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+cp gpurun_out/step_trace.txt gpurun_out/step_trace_8gpu.txt
 python - <<'PY'
 import json
-for n in ("8gpu_c3", "8gpu_c4", "4gpu_c3", "8gpu_c3_nccl", "1gpu_c3_ref", "1gpu_c4_ref"):
+for n in ("8gpu_c3", "8gpu_c3_noplanoverlap", "8gpu_c4", "4gpu_c3"):
     try:
         d = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
         print(n, d["n_gpus"], "ms/step", round(d["ms_per_step"], 4), "value", f'{d["value"]:.4g}', d.get("regions_ms_per_step"))
