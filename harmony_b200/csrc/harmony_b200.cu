@@ -287,6 +287,7 @@ struct hb_handle {
   DevBuf<float> ring, acc2, Psave, OEend, tmpT;  // persistent update kernel state
   DevBuf<double> obj2;
   DevBuf<unsigned> bar;
+  DevBuf<unsigned long long> scan_state;  // chained scan of the plan's histograms: [plan_batch][1 + tiles]
   DevBuf<long long> dbg;  // optional step-phase timestamps (HB_TRACE_STEPS=<cta>)
   int dbg_cta = -1;
   int plan_rounds = 0;   // rounds each plan buffer set holds (two sets: current call / prebuilt next call)
@@ -761,8 +762,13 @@ int plan_sort(hb_handle* h, int t, int nt, bool last_has_next, int set, cudaStre
                                                                    h->chunk_nq.p, nc, nb, nsub, h->H.p, h->err_flag.p, n,
                                                                    with_next);
   CKL();
-  k_scan_exclusive<<<nt, 1024, 0, st>>>(h->H.p, (int64_t)nb * nsub * nc, nullptr);
-  CKL();
+  {  // offsets of the counting sort: chained multi-CTA scan of the nt histograms (a single CTA per round took ~145 us)
+    const int64_t hn = (int64_t)nb * nsub * nc;
+    const int tiles = (int)((hn + SCAN_TILE - 1) / SCAN_TILE);
+    CK(cudaMemsetAsync(h->scan_state.p, 0, sizeof(unsigned long long) * (size_t)nt * (tiles + 1), st));
+    k_scan_chained<<<dim3(tiles, nt), 1024, 0, st>>>(h->H.p, hn, h->scan_state.p, tiles);
+    CKL();
+  }
   k_plan_scatter<<<dim3((nc + wpb - 1) / wpb, nt), wpb * 32, sm, st>>>(
       blk_of, nullptr, h->chunk_start.p, h->chunk_q0.p, h->chunk_nq.p, nc, nb, nsub, h->H.p, order, nullptr,
       (h->use_v2 && !h->use_v4) ? h->prev_at.p + (R0 + t) * n : nullptr, h->use_v4 ? h->next_at.p + (R0 + t) * n : nullptr, n,
@@ -1986,6 +1992,7 @@ int hb_setup(hb_handle* h, const double* Z, int d, int64_t N, const int32_t* phi
     const size_t per_round = (size_t)h->nb * h->plan_nsub * h->nchunks;
     h->plan_batch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)Tplan, ((size_t)16 << 20) / std::max<size_t>(1, per_round)}));
     CK(h->H.alloc(per_round * h->plan_batch));
+    CK(h->scan_state.alloc((size_t)h->plan_batch * ((per_round + SCAN_TILE - 1) / SCAN_TILE + 1)));
   }
   CK(h->chunk_q0.alloc(h->nchunks));
   CK(h->chunk_nq.alloc(h->nchunks));

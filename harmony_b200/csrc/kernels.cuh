@@ -659,6 +659,73 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data,
   }
   if (tid == 0 && total) *total = carry_all;
 }
+// Exclusive scan of `nseg` independent int arrays of n elements (back to back in `data`, in place) by many CTAs:
+// chained scan with dynamic tile numbers.  A CTA draws the next tile (8192 elements) of its segment from a counter
+// — so a tile's predecessor has always been drawn, i.e. runs or has run: no deadlock whatever the dispatch order —,
+// scans it locally, waits for the inclusive prefix of the tile before it, publishes its own (value and flag in one
+// 64-bit word) and writes the results.  state: [nseg][1 + tiles] words, zeroed by the caller (word 0: the counter).
+constexpr int SCAN_TILE = 8192;  // 1024 threads x 8 elements
+__global__ void __launch_bounds__(1024) k_scan_chained(int* __restrict__ data, int64_t n, unsigned long long* __restrict__ state,
+                                                       int tiles_per_seg) {
+  __shared__ int wsum[32];
+  __shared__ int sh_tile, sh_carry;
+  const int seg = blockIdx.y;
+  data += (size_t)seg * (size_t)n;
+  unsigned long long* st = state + (size_t)seg * (tiles_per_seg + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sh_tile = (int)atomicAdd(st, 1ull);
+  __syncthreads();
+  const int tile = sh_tile;
+  if (tile >= tiles_per_seg) return;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)tid * 8;
+  int v[8];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = (base + i < n) ? data[base + i] : 0;
+    s += v[i];
+  }
+  // exclusive scan of the threads' sums within the CTA
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = wsum[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    wsum[lane] = winc - w;  // exclusive prefix of the warps
+    if (lane == 31) {
+      // tile aggregate = winc; chain: inclusive prefix of this tile = prefix of the previous one + aggregate
+      int carry = 0;
+      if (tile > 0) {
+        unsigned long long p;
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(p) : "l"(st + tile) : "memory");  // word 1 + (tile - 1)
+        } while ((p >> 32) == 0ull);
+        carry = (int)(unsigned)(p & 0xffffffffull);
+      }
+      const unsigned long long mine = (1ull << 32) | (unsigned)(carry + winc);
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(st + tile + 1), "l"(mine) : "memory");
+      sh_carry = carry;
+    }
+  }
+  __syncthreads();
+  int run = sh_carry + wsum[warp] + (inc - s);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (base + i < n) data[base + i] = run;
+    run += v[i];
+  }
+}
 // Stable scatter: order[offset(key, chunk) + rank] = cell, cells of a chunk visited in ascending order;
 // next_at[same position] = block of the cell in the next round.
 __global__ void k_plan_scatter(const int* __restrict__ blk_of, const int* __restrict__ blk_next,

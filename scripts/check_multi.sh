@@ -13,10 +13,15 @@ for mode in xch nccl; do
     bench.py --gpus $N --steps 10 --warmup 3 --no-e2e --no-cpu-baseline $KS > gpurun_out/bench_${N}gpu_${mode}.json 2> gpurun_out/bench_${N}gpu_${mode}.err
   tail -3 gpurun_out/bench_${N}gpu_${mode}.err
 done
+for v in "" "--kernel-set 16"; do
+  tag=c4$(echo $v | tr -d ' -')
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 \
+    bench.py --gpus $N --config c4 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline $v > gpurun_out/bench_${N}gpu_${tag}.json 2> gpurun_out/bench_${N}gpu_${tag}.err
+done
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_1gpu_ref.json
 python - <<PY
 import json
-for n in ("${N}gpu_xch", "${N}gpu_nccl", "1gpu_ref"):
+for n in ("${N}gpu_xch", "${N}gpu_nccl", "${N}gpu_c4", "${N}gpu_c4kernelset16", "1gpu_ref"):
     try:
         d = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
         print(n, d["n_gpus"], "ms/step", round(d["ms_per_step"], 4), "value", f'{d["value"]:.4g}', d.get("regions_ms_per_step"))
