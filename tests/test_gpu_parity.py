@@ -16,7 +16,10 @@ of the same algorithm AND no further from the fp32 oracle than that oracle is fr
 Hard cluster indices, explicitly (VERDICT r1 "weak" 2): against BOTH oracles every cell whose hard index
 differs must be a near-tie of that oracle (top-2 gap <= ARGMAX_GAP_MAX), and the number of such cells is
 bounded by ARGMAX_FRAC_MAX of the cells.  Calibration on the CPU: the fp32 oracle itself differs from the
-fp64 one in 0 / 4 / 5 cells of 20k / 40k / 30k with gaps up to 1.8e-4.
+fp64 one in 0 / 4 / 5 cells of 20k / 40k / 30k with gaps up to 1.8e-4.  Against the fp32 oracle both bounds
+widen by that oracle's own deviation from fp64 (its flips are added to the count, twice its max |dR| bounds the
+gap): with 200k cells per block its sequential sums drift to max |dR| 4e-2 and ~740 flips of 600k cells
+(`synthetic_big_blocks`) while the GPU path stays at 2e-4 / 6 cells of the fp64 truth.
 """
 import numpy as np
 import pytest
@@ -70,12 +73,16 @@ def argmax_report(Rg, Ro):
     return int(m.sum()), float((part[:, -1] - part[:, -2]).max())
 
 
-def assert_argmax_bounded(Rg, Ro, label):
+def assert_argmax_bounded(Rg, Ro, label, own_flips=0, own_dev=0.0):
+    """`own_flips` / `own_dev`: hard-index flips and max |dR| of the oracle instance `Ro` against the fp64 truth;
+    they widen the bounds, so that an fp32 oracle that has drifted itself (long sequential sums at several
+    100k cells per block) is not held against the GPU path."""
     n, gap = argmax_report(Rg, Ro)
-    limit = max(1, int(np.ceil(ARGMAX_FRAC_MAX * Rg.shape[0])))
-    print(f"[{label}] hard-index mismatches: {n} of {Rg.shape[0]} (limit {limit}), largest oracle top-2 gap among them {gap:.2e}")
+    limit = max(1, int(np.ceil(ARGMAX_FRAC_MAX * Rg.shape[0]))) + own_flips
+    gap_max = max(ARGMAX_GAP_MAX, 2 * own_dev)
+    print(f"[{label}] hard-index mismatches: {n} of {Rg.shape[0]} (limit {limit}), largest oracle top-2 gap among them {gap:.2e} (limit {gap_max:.2e})")
     assert n <= limit, (label, n, limit)
-    assert gap <= ARGMAX_GAP_MAX, (label, gap)
+    assert gap <= gap_max, (label, gap, gap_max)
     return n
 
 
@@ -101,7 +108,7 @@ def compare(g, o32, o64, label):
         assert e_g64 <= TOL_Z and e_g32 <= e_3264 + 1e-5, (e_g64, e_g32, e_3264)
     assert e_g64 <= 2 * e_3264 + 2e-5
     assert bad == 0
-    assert_argmax_bounded(Rg, R32, label + " vs oracle32")
+    assert_argmax_bounded(Rg, R32, label + " vs oracle32", own_flips=argmax_report(R32, R64)[0], own_dev=dR3264)
     assert_argmax_bounded(Rg, R64, label + " vs oracle64")
     # the fp32 oracle carries the reference's own sequential-sum noise: judge R against the fp64 truth
     assert dR64 <= 2 * dR3264 + 1e-5, (dR64, dR3264)
@@ -145,6 +152,10 @@ CASES = {
     "synthetic_K128": lambda: (synthetic(12000, 24, [6], n_types=20, seed=10), "cov0", dict(nclust=128)),
     "synthetic_blocksize_001": lambda: (synthetic(20000, 20, [4], n_types=12, seed=11), "cov0",
                                         dict(nclust=100, options=harmony_options(block_size=0.01))),
+    # few, large blocks: 600k cells in 3 blocks -> ~1380 rows per CTA and block step, 86 per warp: the prefetch cursor
+    # of the update kernel walks several 32-row plan windows per step (config 3 has 21 rows per warp: one window)
+    "synthetic_big_blocks": lambda: (synthetic(600000, 8, [3], n_types=6, seed=13), "cov0",
+                                     dict(nclust=12, options=harmony_options(block_size=0.34, max_iter_cluster=3))),
     # legacy usage: many clustering rounds per call (max.iter.cluster = 40 > 31)
     "synthetic_T40": lambda: (synthetic(3000, 12, [3], seed=12), "cov0",
                               dict(nclust=10, options=harmony_options(max_iter_cluster=40, epsilon_cluster=-np.inf))),

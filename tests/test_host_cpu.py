@@ -182,3 +182,35 @@ def test_host_widen_pool_matches_numpy():
         nthreads = nthreads or t
         assert t == nthreads and t >= 1
         assert np.array_equal(out, src.astype(np.float64))
+
+
+def test_bench_workloads_are_well_formed():
+    """bench.py's synthetic shards of BASELINE.json configs 3 / 4 / 5: level ids per covariate in range, further
+    covariates nested in the first (J = number of donors), shards consistent for any split, setup arguments in the
+    global level numbering of R/ui.R:219-231."""
+    import bench
+    saved = dict(bench.W)
+    try:
+        for cid, J_expected in (("c3", 20), ("c4", 40), ("c5", 40)):
+            bench.W.clear()
+            bench.W.update(bench.WORKLOADS[cid])
+            B_vec = bench.W["B_vec"]
+            Z, lv = bench.synth_shard(30000, 0, 7)
+            assert Z.shape == (30000, bench.W["d"]) and lv.shape == (30000, len(B_vec))
+            for c, b in enumerate(B_vec):
+                assert lv[:, c].min() >= 0 and lv[:, c].max() < b
+            assert len(np.unique(lv, axis=0)) == J_expected
+            if len(B_vec) > 1:   # every donor belongs to one dataset; a third covariate is a property of the donor
+                for donor in range(B_vec[1]):
+                    assert len(np.unique(lv[lv[:, 1] == donor, 0])) <= 1
+                    if len(B_vec) > 2:
+                        assert len(np.unique(lv[lv[:, 1] == donor, 2])) <= 1
+            Za, la = bench.synth_shard(10000, 0, 7)
+            Zb, lb = bench.synth_shard(10000, 0, 7)
+            np.testing.assert_array_equal(Za, Zb)                      # deterministic in (seed, offset)
+            kw = bench.setup_kwargs(lv)
+            assert kw["phi"].max() < sum(B_vec) and len(kw["theta"]) == sum(B_vec) and kw["K"] == bench.W["K"]
+            assert bench.algo_bytes_per_cell_iter(100, 50) == 6224 and bench.algo_bytes_per_cell_iter(200, 100) == 12424
+    finally:
+        bench.W.clear()
+        bench.W.update(saved)
