@@ -92,7 +92,7 @@ struct Region {
 
 // ---- host worker pool: widens float -> double into caller memory with several threads ---------------------
 // A device -> host copy into pageable memory runs at the speed of one driver thread that also takes the page
-// faults of a freshly allocated destination.  The threaded download path (HB_DOWNLOAD_MT=1) instead DMA's
+// faults of a freshly allocated destination.  The download path (hb_get_field) instead DMA's
 // floats into pinned staging and lets this pool widen + scatter them while the next chunk is in flight.
 class WidenPool {
  public:

@@ -156,7 +156,7 @@ int hb_enable_timing(hb_handle* h, int on);
  * (inverse = 1) in the keyed pseudo-random order of n cells that replaces arma::shuffle (harmony.cpp:272-273)
  * when no update order is injected.  Returns ~0 for i >= n. */
 uint64_t hb_debug_permute(uint64_t i, uint64_t n, uint64_t key, int inverse);
-/* Test hook (host only): the host worker pool of the threaded download path (HB_DOWNLOAD_MT=1) widens n floats to
+/* Test hook (host only): the host worker pool of the download path (hb_get_field) widens n floats to
  * doubles; `threads` sizes the pool on first use (<= 0: HB_HOST_THREADS or the core count).  Returns the pool size. */
 int hb_debug_widen(double* out, const float* in, int64_t n, int threads);
 /* Test hooks of the native kmeans_centers (hb_init_cluster(h, NULL); utils.cpp:10-64): the keyed-hash uniform that

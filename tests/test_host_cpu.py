@@ -169,7 +169,7 @@ def test_update_kernel_ring_geometry():
 
 
 def test_host_widen_pool_matches_numpy():
-    """The worker pool of the threaded download path (HB_DOWNLOAD_MT=1) widens float32 to float64 exactly, for
+    """The worker pool of the download path widens float32 to float64 exactly, for
     sizes around its slice boundaries and repeatedly (the pool is persistent)."""
     import ctypes
     L = _lib.lib()
@@ -214,3 +214,25 @@ def test_bench_workloads_are_well_formed():
     finally:
         bench.W.clear()
         bench.W.update(saved)
+
+
+def test_c_host_builds_against_the_header_and_fails_loudly_without_a_device(tmp_path):
+    """`include/harmony_b200.h` is plain C99 and a C host (examples/harmonize.c: the reference's harmonize() loop
+    on the C ABI alone) links against the in-tree library; without a CUDA device it stops at hb_create."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.lib()   # builds the library if it is missing
+    exe = str(tmp_path / "harmonize_demo")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I", os.path.join(_lib.ROOT, "include"),
+           os.path.join(_lib.ROOT, "examples", "harmonize.c"), "-L", _lib._HERE, "-lharmony_b200",
+           "-Wl,-rpath," + _lib._HERE, "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        return   # running it is the GPU box's business (scripts/check_gpu.sh)
+    r = subprocess.run([exe, "1000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3, (r.returncode, r.stderr)
+    assert "no usable CUDA device" in r.stderr
