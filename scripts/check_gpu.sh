@@ -27,3 +27,7 @@ for n in ("c3", "c4", "c5"):
     except Exception as e:
         print(n, "failed:", e)
 PY
+# the driver loop from plain C (examples/harmonize.c) and the tcgen05 descriptor address-map probes
+gcc -std=c99 -O2 -Iinclude examples/harmonize.c -Lharmony_b200 -lharmony_b200 -Wl,-rpath,$PWD/harmony_b200 -lm -o gpurun_out/harmonize_demo \
+  && timeout 120 gpurun_out/harmonize_demo 200000 > gpurun_out/harmonize_demo.txt 2>&1; tail -4 gpurun_out/harmonize_demo.txt
+timeout 200 bash scripts/mb/run_layout_probe.sh gpurun_out/umma_layout_probe.txt; head -12 gpurun_out/umma_layout_probe.txt
