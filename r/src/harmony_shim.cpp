@@ -2,7 +2,9 @@
 // names as the reference (/root/reference/src/harmony.cpp:672-709), every body a marshalling call into the
 // C ABI of include/harmony_b200.h (libharmony_b200.so).  No RcppArmadillo on the hot path.
 //
-// SOURCE ONLY: this image has no R / Rcpp, so the file is not compiled or tested here.
+// SOURCE ONLY as an R module: this image has no R / Rcpp.  The CPU suite type-checks it against
+// include/harmony_b200.h with an API-shaped stand-in for the few Rcpp types it uses (tests/stubs/Rcpp.h), links it to
+// the in-tree library and drives it to its first library call (tests/test_host_cpu.py).
 // Build (on a machine with R): R CMD SHLIB harmony_shim.cpp -I../../include -L<libdir> -lharmony_b200
 // and keep R/harmony-package.R's `loadModule("harmony_module", TRUE)` unchanged.
 #include <Rcpp.h>
@@ -13,8 +15,8 @@ using namespace Rcpp;
 
 static void hb_check(hb_handle* h, int st) {
   char buf[512];
-  while (hb_pop_warning(h, buf, sizeof(buf))) Rcpp::warning(buf);      // harmony.cpp:86-88
-  if (st > 0) Rcpp::stop(hb_last_error(h));                             // harmony.cpp:83-85, arma::inv failures
+  while (hb_pop_warning(h, buf, sizeof(buf))) Rcpp::warning("%s", buf);  // harmony.cpp:86-88
+  if (st > 0) Rcpp::stop("%s", hb_last_error(h));                         // harmony.cpp:83-85, arma::inv failures
 }
 
 class harmony {
@@ -39,6 +41,7 @@ class harmony {
                           lam, alpha, max_iter_kmeans, epsilon_kmeans, epsilon_harmony, K, block_size,
                           batch_proportion_cutoff, verbose));
     // R's RNG seeds the native generators so that set.seed() keeps runs reproducible (R/ui.R:263-266)
+    Rcpp::RNGScope rng;   // GetRNGstate / PutRNGstate around the draw (module methods get no implicit scope)
     hb_set_seed(h_, (uint64_t)(R::unif_rand() * 9007199254740992.0));
     hb_set_abort_callback(h_, &harmony::check_abort, nullptr);
   }
@@ -51,7 +54,7 @@ class harmony {
   void moe_correct_ridge_cpp() { hb_check(h_, hb_moe_correct_ridge(h_)); }
   bool check_convergence(int type) {
     int r = hb_check_convergence(h_, type);
-    if (r < 0) Rcpp::stop(hb_last_error(h_));
+    if (r < 0) Rcpp::stop("%s", hb_last_error(h_));
     return r != 0;
   }
   void compute_objective() { hb_check(h_, hb_compute_objective(h_)); }
@@ -81,13 +84,15 @@ class harmony {
   int get_max_iter_kmeans() { return dim(HB_MAX_ITER_KMEANS); }
   void set_max_iter_kmeans(int v) { hb_check(h_, hb_set_scalar(h_, HB_MAX_ITER_KMEANS, v)); }  // walkthrough.Rmd:364
   void set_alpha(double v) { hb_check(h_, hb_set_scalar(h_, HB_ALPHA, v)); }
-  void set_Y(const NumericMatrix& m) { hb_check(h_, hb_set_field(h_, HB_Y, m.begin())); }
-  void set_R(const NumericMatrix& m) { hb_check(h_, hb_set_field(h_, HB_R, m.begin())); }
-  void set_O(const NumericMatrix& m) { hb_check(h_, hb_set_field(h_, HB_O, m.begin())); }
-  void set_E(const NumericMatrix& m) { hb_check(h_, hb_set_field(h_, HB_E, m.begin())); }
-  void set_theta(const NumericVector& v) { hb_check(h_, hb_set_field(h_, HB_THETA, v.begin())); }
-  void set_sigma(const NumericVector& v) { hb_check(h_, hb_set_field(h_, HB_SIGMA, v.begin())); }
-  void set_lambda(const NumericVector& v) { hb_check(h_, hb_set_field(h_, HB_LAMBDA_VEC, v.begin())); }
+  // setters take their value the way Rcpp's .property(name, get, set) requires: `void (Class::*)(PROP)` with the
+  // getter's PROP (an Rcpp matrix / vector is a cheap proxy of the SEXP)
+  void set_Y(NumericMatrix m) { hb_check(h_, hb_set_field(h_, HB_Y, m.begin())); }
+  void set_R(NumericMatrix m) { hb_check(h_, hb_set_field(h_, HB_R, m.begin())); }
+  void set_O(NumericMatrix m) { hb_check(h_, hb_set_field(h_, HB_O, m.begin())); }
+  void set_E(NumericMatrix m) { hb_check(h_, hb_set_field(h_, HB_E, m.begin())); }
+  void set_theta(NumericVector v) { hb_check(h_, hb_set_field(h_, HB_THETA, v.begin())); }
+  void set_sigma(NumericVector v) { hb_check(h_, hb_set_field(h_, HB_SIGMA, v.begin())); }
+  void set_lambda(NumericVector v) { hb_check(h_, hb_set_field(h_, HB_LAMBDA_VEC, v.begin())); }
   std::vector<double> trace(int id) {
     int64_t n = hb_trace(h_, id, nullptr, 0);
     std::vector<double> v(n > 0 ? n : 0);

@@ -236,3 +236,36 @@ def test_c_host_builds_against_the_header_and_fails_loudly_without_a_device(tmp_
     r = subprocess.run([exe, "1000"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 3, (r.returncode, r.stderr)
     assert "no usable CUDA device" in r.stderr
+
+
+# names the reference's Rcpp module exposes (src/harmony.cpp:672-709: .field / .method of class `harmony`)
+REFERENCE_MODULE_NAMES = """N B K d O E Y Pr_b B_vec alpha W R theta sigma lambda kmeans_rounds objective_kmeans
+objective_kmeans_dist objective_kmeans_entropy objective_kmeans_cross objective_harmony max_iter_kmeans getZcorr getZorig
+getLambda getR getCentroids check_convergence setup compute_objective init_cluster_cpp cluster_cpp
+moe_correct_ridge_cpp""".split()
+
+
+def test_rcpp_shim_type_checks_against_the_c_abi(tmp_path):
+    """r/src/harmony_shim.cpp cannot be built as an R module here (no R / Rcpp); it is at least type-checked against
+    include/harmony_b200.h through an API-shaped stand-in for the Rcpp types it uses (tests/stubs/Rcpp.h), linked to
+    the in-tree library, its module registration run (same names as the reference's module) and its constructor
+    driven to the library's no-device error."""
+    import shutil
+    import subprocess
+    import torch
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    _lib.lib()
+    exe = str(tmp_path / "shim_driver")
+    root = _lib.ROOT
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "tests", "stubs"),
+           "-I", os.path.join(root, "include"), "-I", os.path.join(root, "r", "src"),
+           os.path.join(root, "tests", "stubs", "shim_driver.cpp"), "-L", _lib._HERE, "-lharmony_b200",
+           "-Wl,-rpath," + _lib._HERE, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    exposed = [ln.split()[-1] for ln in r.stdout.splitlines() if ln.startswith(("property", "method"))]
+    assert sorted(exposed) == sorted(REFERENCE_MODULE_NAMES)
+    if not torch.cuda.is_available():
+        assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
